@@ -1,0 +1,170 @@
+/*
+ * sequnwinder_b200.h — C ABI of libsequnwinder_b200.so (sm_100a CUDA), the drop-in for
+ * SeqUnwinder's two data-parallel hot paths. Plain pointers and sizes only; every entry point
+ * names the reference interface it replaces. Citations are relative to
+ * /root/reference/src/org/seqcode/projects/sequnwinder/. The Java-side JNI stubs that bind these
+ * symbols are shown in INTEGRATION.md.
+ *
+ * Conventions: every function returns SQW_OK (0) or a negative SQW_ERR_* code; the message for
+ * the calling thread's last failure is sqw_last_error(). There is NO CPU fallback: without a
+ * CUDA device every compute entry point fails with SQW_ERR_NO_DEVICE.
+ * "host" variants take host buffers and do their own H2D/D2H copies (this is what the Java
+ * host calls); "_dev" variants take device pointers and a cudaStream_t (as void*) and never
+ * synchronise, so featurisation -> training can stay resident in HBM.
+ */
+#ifndef SEQUNWINDER_B200_H
+#define SEQUNWINDER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SQW_OK 0
+#define SQW_ERR_INVALID_ARG (-1)
+#define SQW_ERR_NO_DEVICE (-2)
+#define SQW_ERR_CUDA (-3)
+#define SQW_ERR_BAD_BASE (-4)     /* seqcode-core seq2int's IllegalArgumentException */
+#define SQW_ERR_UNSUPPORTED (-5)
+#define SQW_ERR_NUMERIC (-6)      /* NaN/Inf met by the solver (LBFGS.java:792-814 guards) */
+#define SQW_ERR_NCCL (-7)
+#define SQW_ERR_STATE (-8)        /* call sequence violated (e.g. execute before set_problem) */
+
+#define SQW_ABI_VERSION 1
+
+int sqw_abi_version(void);
+const char *sqw_last_error(void);
+/* number of visible CUDA devices (0 when there is none); never fails */
+int sqw_device_count(void);
+/* bind the calling thread (and handles created afterwards) to a device */
+int sqw_set_device(int device);
+
+/* ------------------------------------------------------------------------------------------
+ * Path 1 — k-mer featurisation.
+ * Replaces loaddata/MakeArff.java:314-377 (KmerCounter.printPeakSeqKmerRange) and its second
+ * copy utils/ScoreSites.java:105-116.
+ * ---------------------------------------------------------------------------------------- */
+
+/* numK = sum_{k=kmin..kmax} 4^k (MakeArff.java:325-328); -1 on invalid range */
+int64_t sqw_num_kmers(int kmin, int kmax);
+
+/* Host entry point.
+ *   bases   : concatenated ASCII sequences (upper or lower case), sum of lengths bytes
+ *   offsets : n+1 start offsets into bases (sequence r = bases[offsets[r] .. offsets[r+1]))
+ *   counts  : out, n x numK int32 row-major; column = base_k + min(fwd, revcomp) with
+ *             base_k = sum_{j<k} 4^j for j>=kmin (MakeArff.java:357-367)
+ *   has_n   : out, n bytes; 1 when the sequence contains 'N' (MakeArff.java:354-355: the caller
+ *             must omit the row; its counts are returned as zeros)
+ * Returns SQW_ERR_BAD_BASE if any sequence holds a character outside ACGTN. */
+int sqw_kmer_count(const char *bases, const int64_t *offsets, int64_t n, int kmin, int kmax,
+                   int32_t *counts, uint8_t *has_n);
+
+/* Device-resident entry point: all pointers are device pointers, launch is asynchronous on
+ * `stream`. max_len = longest sequence (bases). d_status: one int32, OR-ed with 1 when a
+ * character outside ACGTN was met (caller zeroes it and reads it back). */
+int sqw_kmer_count_dev(const uint8_t *d_bases, const int64_t *d_offsets, int64_t n,
+                       int64_t max_len, int kmin, int kmax, int32_t *d_counts, uint8_t *d_has_n,
+                       int32_t *d_status, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Path 2 — consensus-ADMM trainer.
+ * Replaces framework/LOne.java (an framework/Optimizer.java:5-27 plug-in) together with its
+ * inner solver framework/LBFGS.java + Mcsrch.java. Call order mirrors
+ * framework/Classifier.java:422-449:
+ *   create -> set_problem -> set_structure -> set_params -> [set_comm] -> execute -> destroy
+ * ---------------------------------------------------------------------------------------- */
+typedef struct sqw_admm sqw_admm;
+
+/* new LOne(...) (LOne.java:110-114) */
+int sqw_admm_create(sqw_admm **out);
+/* clearOptimizer() (LOne.java:259-263) */
+void sqw_admm_destroy(sqw_admm *h);
+
+/* LOne(xinit, sm_xinit, data) + setClsMembership + setInstanceWeights + setNumClasses +
+ * setNumPredictors (LOne.java:95-98,110-114).
+ *   data : n_rows x dim row-major fp64, column 0 == 1, already standardised
+ *          (Classifier.java:337-381); y: class of each row (0..num_classes-1); w: weights.
+ * Host variant copies to the device; _dev variant borrows device pointers (they must stay
+ * valid until destroy). Multi-GPU: every rank passes the FULL problem to the host variant
+ * (only the rows of its own ADMM blocks are uploaded), see sqw_admm_set_comm. */
+int sqw_admm_set_problem(sqw_admm *h, int64_t n_rows, int32_t dim, int32_t num_classes,
+                         const double *data, const int32_t *y, const double *w);
+int sqw_admm_set_problem_dev(sqw_admm *h, int64_t n_rows, int32_t dim, int32_t num_classes,
+                             const double *d_data, const int32_t *d_y, const double *d_w);
+
+/* setClassStructure (LOne.java:99; Classifier.java:633-736), CSR arrays with one entry per
+ * design-file line in file order. Parents are meaningful for leaves only, children for
+ * non-leaves only (Classifier.java:665,672). Leaves must carry indices 0..num_classes-1. */
+int sqw_admm_set_structure(sqw_admm *h, int32_t num_nodes, int32_t num_layers,
+                           const int32_t *node_index, const int32_t *is_leaf,
+                           const int32_t *layer, const int32_t *parent_ptr,
+                           const int32_t *parent_idx, const int32_t *child_ptr,
+                           const int32_t *child_idx);
+
+/* setRidge, setPho, set_numThreads, setADMMmaxItrs, setSeqUnwinderMaxIts, setDebugMode
+ * (LOne.java:92-104). num_threads is T, the number of ADMM row blocks — it fixes the numerics
+ * (row i -> block i % T, rows >= floor(N/T)*T dropped, LOne.java:337-357), not the number of
+ * host threads or GPUs. */
+int sqw_admm_set_params(sqw_admm *h, double ridge, double pho, int32_t num_threads,
+                        int32_t admm_max_itr, int32_t nodes_max_itr, int32_t debug);
+
+/* Multi-GPU (one process per GPU): blocks t with t % world == rank live on this rank; the
+ * consensus sums (LOne.java:395-417) become one ncclAllReduce per ADMM iteration.
+ * nccl_id is the 128-byte ncclUniqueId produced by sqw_nccl_unique_id on rank 0 and
+ * distributed by the caller (e.g. torch.distributed broadcast). world == 1 needs no call. */
+int sqw_nccl_unique_id(uint8_t id_out[128]);
+int sqw_admm_set_comm(sqw_admm *h, int32_t rank, int32_t world, const uint8_t nccl_id[128]);
+
+/* initUandZ() + execute() + getX() + getsmX() (LOne.java:80-85,116-204,107-108).
+ * x: num_classes*dim, sm_x: num_nodes*dim; both hold the initial values on entry
+ * (Classifier.java:400-420) and the trained values on return, host memory. */
+int sqw_admm_execute(sqw_admm *h, double *x_inout, double *smx_inout);
+
+/* What the reference only prints in -DEBUG mode (LOne.java:129-190,609-610,749-751), plus the
+ * counters the benchmarks need. Valid after execute. */
+typedef struct {
+    int32_t outer_iters;      /* label-consensus iterations executed (LOne.java:119) */
+    int32_t converged;        /* outer convergence flag (LOne.java:176-180) */
+    int32_t ran_admm;         /* LOne.ranADMM at exit */
+    int32_t total_admm_iters; /* sum over outer iterations of ADMM_currItr_value at exit */
+    int64_t total_evals;      /* (objective, gradient) evaluations executed, all local blocks */
+    double final_pho;
+    double final_fold;
+    double seconds_admm;      /* device time inside the ADMM loops (CUDA events), seconds */
+    double seconds_total;     /* device time of the whole execute */
+    int64_t launches;         /* kernels launched by execute */
+    double seconds_eval;      /* device time of the x-update kernels only */
+    int64_t eval_bytes;       /* algorithmic bytes read by those kernels */
+} sqw_admm_stats;
+int sqw_admm_get_stats(const sqw_admm *h, sqw_admm_stats *out);
+
+/* Per-ADMM-iteration log: rows = number of consensus updates executed; arrays may be NULL.
+ * outer/itr: iteration indices; pho/fold: values the x-update of that iteration used;
+ * primal/dual: sums of history_primal/history_dual rows (LOne.java:519-522);
+ * nfev: [rows x num_local_blocks] f/g evaluations per local block. */
+int sqw_admm_get_log(const sqw_admm *h, int32_t cap, int32_t *rows_out, int32_t *outer,
+                     int32_t *itr, double *pho, double *fold, double *primal, double *dual,
+                     int32_t *nfev, int32_t *admm_iters_per_outer);
+
+/* ------------------------------------------------------------------------------------------
+ * Building blocks exposed for parity tests and micro-benchmarks (same kernels execute() uses).
+ * ---------------------------------------------------------------------------------------- */
+
+/* One (objective, gradient) evaluation of LOne.OptObject (LOne.java:936-1049) for every local
+ * block at the block weights cx[t] (host, [T_local x C*dim]); z/u in compact edge layout are
+ * taken as zero, sm_x as given, i.e. only the data term + augmented term with z=u=0.
+ * f_out: [T_local], g_out: [T_local x C*dim]. Requires set_problem/structure/params. */
+int sqw_admm_eval(sqw_admm *h, const double *cx, const double *smx, double pho, double *f_out,
+                  double *g_out);
+
+/* L-BFGS + Moré–Thuente exactly as driven by LOne.java:865-896, on the test function
+ * f(x) = sum_i 100 (x_{2i+1} - x_{2i}^2)^2 + (1 - x_{2i})^2 (device-side solver state machine,
+ * n even). Returns iflag; nfev_out/iters_out as in the oracle. */
+int sqw_lbfgs_rosenbrock(int32_t n, double *x_inout, double eps, int32_t *nfev_out,
+                         int32_t *iters_out, int32_t *iflag_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEQUNWINDER_B200_H */

@@ -1,0 +1,410 @@
+// kmer_count.cu — path 1: reverse-complement-collapsed k-mer count matrix on sm_100a.
+//
+// Replaces loaddata/MakeArff.java:323-377 (KmerCounter.printPeakSeqKmerRange): for every
+// sequence and every k in [kmin,kmax], every window increments column
+// base_k + min(seq2int(window), seq2int(revcomp(window))) of a dense numK-wide int row
+// (MakeArff.java:357-367). Encoding A0 C1 G2 T3, first base most significant.
+//
+// Kernel design (HBM-write bound: 4*numK bytes out vs ~L bytes in per sequence):
+//   * a group of threads (>= one warp) owns one sequence; the ASCII bases are loaded coalesced,
+//     mapped to 2-bit codes and packed MSB-first into 64-bit words with two warp REDUX.OR
+//     reductions per 32 bases, staged in shared memory;
+//   * a window of any k <= 32 is then two LDS.64 + a funnel shift; its reverse complement for
+//     every k at once is brev + pair swap of the complemented word, so forward and reverse codes
+//     for all k in [kmin,kmax] cost one extraction per position;
+//   * counts go to a per-sequence shared-memory histogram with ATOMS (spread addresses);
+//   * the finished row is streamed to HBM with 16-byte st.global.cs stores and the histogram is
+//     re-zeroed in the same pass.
+// Rows containing 'N' are flagged and written as zeros (the Java caller omits them,
+// MakeArff.java:354-355); any other character raises the status bit (seq2int would throw).
+#include "common.cuh"
+
+#include <algorithm>
+#include <vector>
+
+namespace sqw {
+
+struct KmerParams {
+    const uint8_t *bases;
+    const int64_t *offsets;
+    int64_t n;
+    int kmin, kmax;
+    int64_t numK;
+    int32_t *counts;
+    uint8_t *has_n;
+    int32_t *status;
+    int rows_per_block;
+    int seq_words;  // 64-bit words reserved per sequence (incl. one pad word)
+};
+
+enum : int { kFlagN = 1, kFlagBad = 2 };
+
+__device__ __forceinline__ unsigned long long rev2_64(unsigned long long v)
+{
+    // reverse the order of the 32 two-bit groups of v
+    v = __brevll(v);
+    return ((v >> 1) & 0x5555555555555555ull) | ((v & 0x5555555555555555ull) << 1);
+}
+
+// Pack one sequence into MSB-first 2-bit words; returns flags seen by this thread's warp loop.
+__device__ __forceinline__ void pack_sequence(const uint8_t *__restrict__ seq, int64_t len,
+                                              unsigned long long *__restrict__ words, int t,
+                                              int tpr, int *flag_slot)
+{
+    const int lane = t & 31;
+    const int wg = t >> 5;
+    const int nwarps = tpr >> 5;
+    const int64_t nchunks = (len + 31) >> 5;
+    int flags = 0;
+    for (int64_t c = wg; c < nchunks; c += nwarps) {
+        const int64_t pos = (c << 5) + lane;
+        unsigned ch = (pos < len) ? (unsigned)seq[pos] : (unsigned)'A';
+        const unsigned up = ch & 0xDFu;
+        unsigned code = (up >> 1) & 3u;  // A0 C1 G3 T2
+        code ^= (code >> 1);             // A0 C1 G2 T3
+        const bool ok = (up == 'A') | (up == 'C') | (up == 'G') | (up == 'T');
+        if (!ok) {
+            flags |= (up == 'N') ? kFlagN : kFlagBad;
+            code = 0;
+        }
+        const unsigned sh = 30u - 2u * (unsigned)(lane & 15);
+        const unsigned hi = __reduce_or_sync(0xffffffffu, lane < 16 ? code << sh : 0u);
+        const unsigned lo = __reduce_or_sync(0xffffffffu, lane >= 16 ? code << sh : 0u);
+        if (lane == 0)
+            words[c] = ((unsigned long long)hi << 32) | (unsigned long long)lo;
+    }
+    if (t == 0)
+        words[nchunks] = 0ull;  // pad word read by the funnel shift of the last windows
+    flags = __reduce_or_sync(0xffffffffu, flags);
+    if (lane == 0 && flags)
+        atomicOr(flag_slot, flags);
+}
+
+// One window position: forward code = top 2k bits of `comb`, reverse-complement code = low 2k
+// bits of rev2_64(~comb). Target is either shared (ATOMS) or global (RED) memory.
+template <typename Ptr>
+__device__ __forceinline__ void count_position(const unsigned long long *__restrict__ words,
+                                               int64_t i, int64_t len, int kmin, int kmax,
+                                               Ptr hist)
+{
+    const int64_t w = i >> 5;
+    const int s = (int)(i & 31) << 1;
+    const unsigned long long hi = words[w], lo = words[w + 1];
+    const unsigned long long comb = s ? ((hi << s) | (lo >> (64 - s))) : hi;
+    const unsigned long long rc_all = rev2_64(~comb);
+    int64_t base = 0;
+    for (int k = kmin; k <= kmax; ++k) {
+        if (i + k <= len) {
+            const unsigned long long fwd = comb >> (64 - 2 * k);
+            const unsigned long long rc = (k == 32) ? rc_all : (rc_all & ((1ull << (2 * k)) - 1ull));
+            atomicAdd(hist + base + (int64_t)(fwd < rc ? fwd : rc), 1);
+        }
+        base += (int64_t)1 << (2 * k);
+    }
+}
+
+// Shared-memory histogram path: rows_per_block sequences per CTA, blockDim/rows_per_block
+// threads each, persistent grid-stride loop over row batches.
+__global__ void __launch_bounds__(256) kmer_count_smem_kernel(KmerParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int R = p.rows_per_block;
+    const int tpr = blockDim.x / R;
+    const int g = threadIdx.x / tpr;
+    const int t = threadIdx.x - g * tpr;
+    const int64_t numK = p.numK;
+    int32_t *hist_all = reinterpret_cast<int32_t *>(smem);
+    unsigned long long *words_all =
+        reinterpret_cast<unsigned long long *>(smem + (size_t)R * numK * sizeof(int32_t));
+    int *flags = reinterpret_cast<int *>(words_all + (size_t)R * p.seq_words);
+    int32_t *hist = hist_all + (size_t)g * numK;
+    unsigned long long *words = words_all + (size_t)g * p.seq_words;
+
+    {
+        int4 *h4 = reinterpret_cast<int4 *>(hist_all);
+        const int64_t n4 = (int64_t)R * numK / 4;
+        for (int64_t i = threadIdx.x; i < n4; i += blockDim.x)
+            h4[i] = make_int4(0, 0, 0, 0);
+    }
+
+    const int64_t nbatches = (p.n + R - 1) / R;
+    for (int64_t b = blockIdx.x; b < nbatches; b += gridDim.x) {
+        const int64_t row = b * R + g;
+        const bool valid = row < p.n;
+        int64_t beg = 0, len = 0;
+        if (t == 0)
+            flags[g] = 0;
+        __syncthreads();  // histogram zeroed / re-zeroed, flags cleared
+        if (valid) {
+            beg = p.offsets[row];
+            len = p.offsets[row + 1] - beg;
+            pack_sequence(p.bases + beg, len, words, t, tpr, &flags[g]);
+        }
+        __syncthreads();
+        const int fl = flags[g];
+        if (valid && fl == 0) {
+            for (int64_t i = t; i + p.kmin <= len; i += tpr)
+                count_position(words, i, len, p.kmin, p.kmax, hist);
+        }
+        __syncthreads();
+        if (valid) {
+            int4 *src = reinterpret_cast<int4 *>(hist);
+            int4 *dst = reinterpret_cast<int4 *>(p.counts + row * numK);
+            const int n4 = (int)(numK >> 2);
+            for (int i = t; i < n4; i += tpr) {
+                const int4 v = src[i];
+                __stcs(dst + i, v);
+                if (v.x | v.y | v.z | v.w)
+                    src[i] = make_int4(0, 0, 0, 0);
+            }
+            if (t == 0) {
+                p.has_n[row] = (fl & kFlagN) ? 1 : 0;
+                if ((fl & kFlagBad) && !(fl & kFlagN))
+                    atomicOr(p.status, 1);
+            }
+        }
+    }
+}
+
+// Fallback for histograms that do not fit in shared memory (numK*4 > ~200 KB, i.e. k >= 8):
+// the output is cleared with a memset and one warp per sequence issues global RED.ADDs.
+__global__ void __launch_bounds__(256) kmer_count_global_kernel(KmerParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warps = blockDim.x >> 5;
+    const int g = threadIdx.x >> 5;
+    const int t = threadIdx.x & 31;
+    unsigned long long *words =
+        reinterpret_cast<unsigned long long *>(smem) + (size_t)g * p.seq_words;
+    int *flags = reinterpret_cast<int *>(reinterpret_cast<unsigned long long *>(smem) +
+                                         (size_t)warps * p.seq_words);
+    for (int64_t row = (int64_t)blockIdx.x * warps + g; row < p.n;
+         row += (int64_t)gridDim.x * warps) {
+        if (t == 0)
+            flags[g] = 0;
+        __syncwarp();
+        const int64_t beg = p.offsets[row];
+        const int64_t len = p.offsets[row + 1] - beg;
+        pack_sequence(p.bases + beg, len, words, t, 32, &flags[g]);
+        __syncwarp();
+        const int fl = flags[g];
+        if (fl == 0) {
+            int32_t *out = p.counts + row * p.numK;
+            for (int64_t i = t; i + p.kmin <= len; i += 32)
+                count_position(words, i, len, p.kmin, p.kmax, out);
+        }
+        if (t == 0) {
+            p.has_n[row] = (fl & kFlagN) ? 1 : 0;
+            if ((fl & kFlagBad) && !(fl & kFlagN))
+                atomicOr(p.status, 1);
+        }
+        __syncwarp();
+    }
+}
+
+static int64_t num_kmers(int kmin, int kmax)
+{
+    if (kmin < 1 || kmax < kmin || kmax > 15)
+        return -1;
+    int64_t numK = 0;
+    for (int k = kmin; k <= kmax; ++k)
+        numK += (int64_t)1 << (2 * k);
+    return numK;
+}
+
+static int launch_kmer(const uint8_t *d_bases, const int64_t *d_offsets, int64_t n,
+                       int64_t max_len, int kmin, int kmax, int32_t *d_counts, uint8_t *d_has_n,
+                       int32_t *d_status, cudaStream_t stream)
+{
+    const int64_t numK = num_kmers(kmin, kmax);
+    if (numK < 0)
+        return set_error(SQW_ERR_INVALID_ARG, "invalid k range [%d,%d] (1 <= kmin <= kmax <= 15)",
+                         kmin, kmax);
+    if (n < 0 || max_len < 0)
+        return set_error(SQW_ERR_INVALID_ARG, "negative size");
+    if (n == 0)
+        return SQW_OK;
+    if ((reinterpret_cast<uintptr_t>(d_counts) & 15) != 0)
+        return set_error(SQW_ERR_INVALID_ARG, "counts must be 16-byte aligned");
+
+    KmerParams p;
+    p.bases = d_bases;
+    p.offsets = d_offsets;
+    p.n = n;
+    p.kmin = kmin;
+    p.kmax = kmax;
+    p.numK = numK;
+    p.counts = d_counts;
+    p.has_n = d_has_n;
+    p.status = d_status;
+    p.seq_words = (int)((max_len + 31) / 32 + 1);
+
+    const size_t seq_bytes = (size_t)p.seq_words * 8;
+    const size_t hist_bytes = (size_t)numK * 4;
+    const size_t kMaxSmem = 200 * 1024;
+    const int threads = 256;
+
+    if (hist_bytes + seq_bytes + 16 <= kMaxSmem && (numK % 4) == 0) {
+        // rows per CTA: aim for <= ~48 KB per CTA (4-5 CTAs per SM overlap pack / count / store)
+        int R = 8;
+        while (R > 1 && (size_t)R * (hist_bytes + seq_bytes) + 64 > 56 * 1024)
+            R >>= 1;
+        p.rows_per_block = R;
+        const size_t smem = (size_t)R * (hist_bytes + seq_bytes) + (size_t)R * sizeof(int) + 16;
+        SQW_CUDA_CHECK(cudaFuncSetAttribute(kmer_count_smem_kernel,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)smem));
+        int per_sm = 1;
+        SQW_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+            &per_sm, kmer_count_smem_kernel, threads, smem));
+        if (per_sm < 1)
+            per_sm = 1;
+        const int64_t nbatches = (n + R - 1) / R;
+        const int grid = (int)std::min<int64_t>(nbatches, (int64_t)kNumSMs * per_sm);
+        kmer_count_smem_kernel<<<grid, threads, smem, stream>>>(p);
+    } else {
+        if ((size_t)(threads / 32) * seq_bytes > kMaxSmem)
+            return set_error(SQW_ERR_UNSUPPORTED, "sequence of %lld bases is too long",
+                             (long long)max_len);
+        SQW_CUDA_CHECK(cudaMemsetAsync(d_counts, 0, (size_t)n * numK * 4, stream));
+        p.rows_per_block = threads / 32;
+        const size_t smem = (size_t)(threads / 32) * (seq_bytes + sizeof(int)) + 16;
+        SQW_CUDA_CHECK(cudaFuncSetAttribute(kmer_count_global_kernel,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)smem));
+        const int64_t nb = (n + threads / 32 - 1) / (threads / 32);
+        const int grid = (int)std::min<int64_t>(nb, (int64_t)kNumSMs * 8);
+        kmer_count_global_kernel<<<grid, threads, smem, stream>>>(p);
+    }
+    SQW_CUDA_CHECK(cudaGetLastError());
+    return SQW_OK;
+}
+
+}  // namespace sqw
+
+extern "C" {
+
+int64_t sqw_num_kmers(int kmin, int kmax) { return sqw::num_kmers(kmin, kmax); }
+
+int sqw_kmer_count_dev(const uint8_t *d_bases, const int64_t *d_offsets, int64_t n,
+                       int64_t max_len, int kmin, int kmax, int32_t *d_counts, uint8_t *d_has_n,
+                       int32_t *d_status, void *stream)
+{
+    int rc = sqw::require_device();
+    if (rc != SQW_OK)
+        return rc;
+    return sqw::launch_kmer(d_bases, d_offsets, n, max_len, kmin, kmax, d_counts, d_has_n,
+                            d_status, static_cast<cudaStream_t>(stream));
+}
+
+int sqw_kmer_count(const char *bases, const int64_t *offsets, int64_t n, int kmin, int kmax,
+                   int32_t *counts, uint8_t *has_n)
+{
+    using namespace sqw;
+    int rc = require_device();
+    if (rc != SQW_OK)
+        return rc;
+    const int64_t numK = num_kmers(kmin, kmax);
+    if (numK < 0)
+        return set_error(SQW_ERR_INVALID_ARG, "invalid k range [%d,%d] (1 <= kmin <= kmax <= 15)",
+                         kmin, kmax);
+    if (n < 0 || (n > 0 && (!offsets || !counts || !has_n)))
+        return set_error(SQW_ERR_INVALID_ARG, "null buffer");
+    if (n == 0)
+        return SQW_OK;
+
+    // Row chunks sized so one chunk's output is <= 512 MiB; two buffers / two streams overlap
+    // the D2H copy of chunk i with the kernel of chunk i+1.
+    const int64_t row_bytes = numK * 4;
+    int64_t chunk_rows = std::max<int64_t>(1, ((int64_t)512 << 20) / row_bytes);
+    chunk_rows = std::min(chunk_rows, n);
+    const int nbuf = (chunk_rows < n) ? 2 : 1;
+
+    int64_t max_len = 0, max_chunk_bases = 0;
+    for (int64_t r = 0; r < n; ++r) {
+        const int64_t len = offsets[r + 1] - offsets[r];
+        if (len < 0)
+            return set_error(SQW_ERR_INVALID_ARG, "offsets must be non-decreasing");
+        max_len = std::max(max_len, len);
+    }
+    for (int64_t r0 = 0; r0 < n; r0 += chunk_rows) {
+        const int64_t r1 = std::min(n, r0 + chunk_rows);
+        max_chunk_bases = std::max(max_chunk_bases, offsets[r1] - offsets[r0]);
+    }
+
+    uint8_t *d_bases[2] = {nullptr, nullptr};
+    int64_t *d_off[2] = {nullptr, nullptr};
+    int32_t *d_counts[2] = {nullptr, nullptr};
+    uint8_t *d_hasn[2] = {nullptr, nullptr};
+    int32_t *d_status = nullptr;
+    cudaStream_t st[2] = {nullptr, nullptr};
+    int result = SQW_OK;
+    std::vector<int64_t> rel((size_t)chunk_rows + 1);
+
+    auto cleanup = [&]() {
+        for (int i = 0; i < 2; ++i) {
+            if (d_bases[i]) cudaFree(d_bases[i]);
+            if (d_off[i]) cudaFree(d_off[i]);
+            if (d_counts[i]) cudaFree(d_counts[i]);
+            if (d_hasn[i]) cudaFree(d_hasn[i]);
+            if (st[i]) cudaStreamDestroy(st[i]);
+        }
+        if (d_status) cudaFree(d_status);
+    };
+#define SQW_TRY(expr)                                                                         \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            result = set_error(SQW_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+            cleanup();                                                                        \
+            return result;                                                                    \
+        }                                                                                     \
+    } while (0)
+
+    SQW_TRY(cudaMalloc(&d_status, sizeof(int32_t)));
+    SQW_TRY(cudaMemset(d_status, 0, sizeof(int32_t)));
+    for (int i = 0; i < nbuf; ++i) {
+        SQW_TRY(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+        SQW_TRY(cudaMalloc(&d_bases[i], (size_t)std::max<int64_t>(max_chunk_bases, 1)));
+        SQW_TRY(cudaMalloc(&d_off[i], (size_t)(chunk_rows + 1) * sizeof(int64_t)));
+        SQW_TRY(cudaMalloc(&d_counts[i], (size_t)chunk_rows * row_bytes));
+        SQW_TRY(cudaMalloc(&d_hasn[i], (size_t)chunk_rows));
+    }
+
+    int buf = 0;
+    for (int64_t r0 = 0; r0 < n; r0 += chunk_rows, buf ^= (nbuf - 1)) {
+        const int64_t r1 = std::min(n, r0 + chunk_rows);
+        const int64_t rows = r1 - r0;
+        const int64_t b0 = offsets[r0], nb = offsets[r1] - offsets[r0];
+        SQW_TRY(cudaStreamSynchronize(st[buf]));  // previous use of this buffer pair is done
+        for (int64_t r = 0; r <= rows; ++r)
+            rel[(size_t)r] = offsets[r0 + r] - b0;
+        if (nb > 0)
+            SQW_TRY(cudaMemcpyAsync(d_bases[buf], bases + b0, (size_t)nb, cudaMemcpyHostToDevice,
+                                    st[buf]));
+        SQW_TRY(cudaMemcpyAsync(d_off[buf], rel.data(), (size_t)(rows + 1) * sizeof(int64_t),
+                                cudaMemcpyHostToDevice, st[buf]));
+        SQW_TRY(cudaStreamSynchronize(st[buf]));  // rel[] is reused by the next chunk
+        rc = launch_kmer(d_bases[buf], d_off[buf], rows, max_len, kmin, kmax, d_counts[buf],
+                         d_hasn[buf], d_status, st[buf]);
+        if (rc != SQW_OK) {
+            cleanup();
+            return rc;
+        }
+        SQW_TRY(cudaMemcpyAsync(counts + r0 * numK, d_counts[buf], (size_t)rows * row_bytes,
+                                cudaMemcpyDeviceToHost, st[buf]));
+        SQW_TRY(cudaMemcpyAsync(has_n + r0, d_hasn[buf], (size_t)rows, cudaMemcpyDeviceToHost,
+                                st[buf]));
+    }
+    for (int i = 0; i < nbuf; ++i)
+        SQW_TRY(cudaStreamSynchronize(st[i]));
+    int32_t status = 0;
+    SQW_TRY(cudaMemcpy(&status, d_status, sizeof(int32_t), cudaMemcpyDeviceToHost));
+#undef SQW_TRY
+    cleanup();
+    if (status & 1)
+        return set_error(SQW_ERR_BAD_BASE, "Nonstandard nucleotide character encountered");
+    return SQW_OK;
+}
+
+}  // extern "C"
