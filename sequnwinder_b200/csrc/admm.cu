@@ -1,0 +1,972 @@
+// admm.cu — host side of path 2 behind the C ABI (include/sequnwinder_b200.h): owns the device
+// state of one LOne instance, enqueues the kernels of admm_kernels.cuh and runs the outer
+// label-consensus loop of LOne.execute (framework/LOne.java:116-204).
+//
+// The host never waits inside an ADMM iteration: iterations are enqueued ahead of the GPU and a
+// small pinned ring of Ctrl snapshots tells the host, a few iterations late, that the device has
+// set Ctrl.done; the kernels of the surplus iterations return immediately.
+#include "admm_kernels.cuh"
+#include "common.cuh"
+
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace sqw {
+
+// ------------------------------------------------------------------ NCCL through dlopen
+struct NcclUid {
+    char internal[128];
+};
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(NcclUid *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclUid, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+
+static NcclApi *nccl_api()
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *nm : names) {
+            api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (api.lib)
+                break;
+        }
+        if (api.lib) {
+            api.GetUniqueId = (int (*)(NcclUid *))dlsym(api.lib, "ncclGetUniqueId");
+            api.CommInitRank = (int (*)(void **, int, NcclUid, int))dlsym(api.lib, "ncclCommInitRank");
+            api.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *,
+                                     cudaStream_t))dlsym(api.lib, "ncclAllReduce");
+            api.CommDestroy = (int (*)(void *))dlsym(api.lib, "ncclCommDestroy");
+            api.GetErrorString = (const char *(*)(int))dlsym(api.lib, "ncclGetErrorString");
+        }
+    }
+    if (!api.lib || !api.GetUniqueId || !api.CommInitRank || !api.AllReduce)
+        return nullptr;
+    return &api;
+}
+
+constexpr int kNcclDouble = 8, kNcclSum = 0;
+
+// java.util.HashMap iteration order of keys "Thread0".."Thread{T-1}" (LOne.java:399,411,427):
+// the order in which the reference sums the per-thread buffers.
+static std::vector<int> java_thread_order(int T)
+{
+    int cap = 16;
+    while (T > (cap * 3) / 4)
+        cap *= 2;
+    std::vector<int> order;
+    for (int b = 0; b < cap; ++b)
+        for (int t = 0; t < T; ++t) {
+            const std::string key = "Thread" + std::to_string(t);
+            uint32_t h = 0;
+            for (char ch : key)
+                h = 31u * h + (uint32_t)(unsigned char)ch;
+            h ^= (h >> 16);
+            if ((int)(h & (uint32_t)(cap - 1)) == b)
+                order.push_back(t);
+        }
+    return order;
+}
+
+constexpr int kRing = 8;       // Ctrl snapshots in flight
+constexpr int kLookahead = 3;  // iterations the host runs ahead of the snapshot it inspects
+
+}  // namespace sqw
+
+using namespace sqw;
+
+struct sqw_admm {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<void *> allocs;
+
+    // params
+    bool have_params = false, have_structure = false, have_problem = false, prepared = false;
+    double ridge = 10.0, pho = 1.7;
+    int T = 5, admm_max_itr = 400, nodes_max_itr = 15, debug = 0;
+
+    // comm
+    int rank = 0, world = 1;
+    void *comm = nullptr;
+
+    // structure (host)
+    int NN = 0, num_layers = 0, C_struct = 0;
+    std::vector<int> edge_leaf, edge_par, leaf_edge_ptr, edge_sum_order;
+    struct Layer {
+        std::vector<int> nodes, nbr_ptr, nbr_idx;
+        int *d_nodes = nullptr, *d_ptr = nullptr, *d_idx = nullptr;
+    };
+    std::vector<Layer> layers;  // index = layer number (0 unused)
+
+    // problem
+    int64_t n_rows = 0;
+    int dim = 0, C = 0;
+    std::vector<int> block_ids;
+
+    AdmmDev dev{};
+    Ctrl *h_ring = nullptr;  // pinned [kRing]
+    cudaEvent_t ev_x0[kRing], ev_x1[kRing], ev_snap[kRing];
+    cudaEvent_t ev_a, ev_b;
+    int kernel_variant = -1;
+    size_t xupdate_smem = 0;
+
+    // results
+    sqw_admm_stats stats{};
+    std::vector<int> log_outer, log_itr, log_nfev, admm_iters;
+    std::vector<double> log_pho, log_fold, log_primal, log_dual;
+
+    template <typename Tp>
+    int dalloc(Tp **p, size_t count, bool zero = true)
+    {
+        const size_t bytes = std::max<size_t>(count, 1) * sizeof(Tp);
+        SQW_CUDA_CHECK(cudaMalloc((void **)p, bytes));
+        allocs.push_back((void *)*p);
+        if (zero)
+            SQW_CUDA_CHECK(cudaMemsetAsync(*p, 0, bytes, stream));
+        return SQW_OK;
+    }
+};
+
+namespace sqw {
+
+typedef void (*XKernel)(AdmmDev);
+typedef void (*EKernel)(AdmmDev, double, double *);
+
+static XKernel xupdate_kernel(int nct, bool wsmem)
+{
+    switch (nct * 2 + (wsmem ? 1 : 0)) {
+    case 3: return admm_xupdate_kernel<1, true>;
+    case 2: return admm_xupdate_kernel<1, false>;
+    case 5: return admm_xupdate_kernel<2, true>;
+    case 4: return admm_xupdate_kernel<2, false>;
+    case 7: return admm_xupdate_kernel<3, true>;
+    case 6: return admm_xupdate_kernel<3, false>;
+    }
+    return nullptr;
+}
+
+static EKernel eval_kernel(int nct, bool wsmem)
+{
+    switch (nct * 2 + (wsmem ? 1 : 0)) {
+    case 3: return admm_eval_kernel<1, true>;
+    case 2: return admm_eval_kernel<1, false>;
+    case 5: return admm_eval_kernel<2, true>;
+    case 4: return admm_eval_kernel<2, false>;
+    case 7: return admm_eval_kernel<3, true>;
+    case 6: return admm_eval_kernel<3, false>;
+    }
+    return nullptr;
+}
+
+static int upload_ints(sqw_admm *h, const std::vector<int> &v, const int **dst)
+{
+    int *p = nullptr;
+    int rc = h->dalloc(&p, v.size(), false);
+    if (rc != SQW_OK)
+        return rc;
+    if (!v.empty())
+        SQW_CUDA_CHECK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice,
+                                       h->stream));
+    *dst = p;
+    return SQW_OK;
+}
+
+// Allocate everything that depends on params + structure + problem sizes.
+static int prepare(sqw_admm *h)
+{
+    if (h->prepared)
+        return SQW_OK;
+    if (!h->have_params || !h->have_structure || !h->have_problem)
+        return set_error(SQW_ERR_STATE, "set_structure, set_params and set_problem must precede this call");
+    if (h->C_struct != h->C)
+        return set_error(SQW_ERR_INVALID_ARG, "structure has %d leaves but num_classes is %d",
+                         h->C_struct, h->C);
+    AdmmDev &D = h->dev;
+    D.C = h->C;
+    D.Cp = (h->C + 7) / 8 * 8;
+    D.E = (int)h->edge_leaf.size();
+    D.NN = h->NN;
+    D.npad = D.C * D.dimp;
+    D.upad = D.E * D.dimp;
+    D.wstride = D.dimp + 8;  // dimp is a multiple of 16 doubles: +64 B makes class rows alternate
+                             // between the two halves of the 128-byte bank window
+    D.world = h->world;
+    D.ridge = h->ridge;
+    const int nct = D.Cp / 8;
+    if (nct > 3)
+        return set_error(SQW_ERR_UNSUPPORTED, "more than 24 leaf classes (%d) not supported yet", D.C);
+    if ((long long)D.Cp * D.dimp * h->dev.T_local > (1ll << 31) - 1 || (long long)D.upad > (1 << 30))
+        return set_error(SQW_ERR_UNSUPPORTED, "problem too large for 32-bit coordinate indices");
+
+    cudaDeviceProp prop;
+    SQW_CUDA_CHECK(cudaGetDeviceProperties(&prop, h->device));
+    const int n_sm = prop.multiProcessorCount;
+    const size_t w_bytes = (size_t)D.Cp * D.wstride * sizeof(double);
+    const bool wsmem = w_bytes <= 160 * 1024;
+    h->xupdate_smem = wsmem ? w_bytes : 0;
+    h->kernel_variant = nct * 2 + (wsmem ? 1 : 0);
+    XKernel xk = xupdate_kernel(nct, wsmem);
+    EKernel ek = eval_kernel(nct, wsmem);
+    SQW_CUDA_CHECK(cudaFuncSetAttribute(xk, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)h->xupdate_smem));
+    SQW_CUDA_CHECK(cudaFuncSetAttribute(ek, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)h->xupdate_smem));
+    int per_sm = 0;
+    SQW_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, xk, kThreads,
+                                                                 h->xupdate_smem));
+    if (per_sm < 1)
+        return set_error(SQW_ERR_UNSUPPORTED, "x-update kernel does not fit on an SM");
+    // one CTA per SM: G CTAs per ADMM block, all T_local groups co-resident
+    int G = n_sm / D.T_local;
+    if (G < 1) {
+        G = 1;
+        if (D.T_local > n_sm * per_sm)
+            return set_error(SQW_ERR_UNSUPPORTED, "%d local ADMM blocks exceed %d co-resident CTAs",
+                             D.T_local, n_sm * per_sm);
+    }
+    const int max_useful = std::max(1, (D.nb + 7) / 8);
+    G = std::min(G, max_useful);
+    D.G = G;
+
+    int rc;
+#define TRY(x)            \
+    do {                  \
+        rc = (x);         \
+        if (rc != SQW_OK) \
+            return rc;    \
+    } while (0)
+    TRY(upload_ints(h, h->edge_leaf, &D.edge_leaf));
+    TRY(upload_ints(h, h->edge_par, &D.edge_par));
+    TRY(upload_ints(h, h->leaf_edge_ptr, &D.leaf_edge_ptr));
+    TRY(upload_ints(h, h->edge_sum_order, &D.edge_sum_order));
+    TRY(upload_ints(h, h->block_ids, &D.block_ids));
+    for (auto &L : h->layers) {
+        const int *p;
+        TRY(upload_ints(h, L.nodes, &p)); L.d_nodes = (int *)p;
+        TRY(upload_ints(h, L.nbr_ptr, &p)); L.d_ptr = (int *)p;
+        TRY(upload_ints(h, L.nbr_idx, &p)); L.d_idx = (int *)p;
+    }
+    const size_t TL = (size_t)D.T_local;
+    TRY(h->dalloc(&D.xbar, (size_t)D.npad));
+    TRY(h->dalloc(&D.ubar, (size_t)D.upad));
+    TRY(h->dalloc(&D.z, (size_t)D.upad));
+    TRY(h->dalloc(&D.zold, (size_t)D.upad));
+    TRY(h->dalloc(&D.smx, (size_t)D.NN * D.dimp));
+    TRY(h->dalloc(&D.smx_old, (size_t)D.NN * D.dimp));
+    TRY(h->dalloc(&D.xt, TL * D.Cp * D.dimp));
+    TRY(h->dalloc(&D.ut, TL * D.upad));
+    TRY(h->dalloc(&D.g, TL * D.npad));
+    TRY(h->dalloc(&D.gold, TL * D.npad));
+    TRY(h->dalloc(&D.d, TL * D.npad));
+    TRY(h->dalloc(&D.wa, TL * D.npad));
+    TRY(h->dalloc(&D.S, TL * kLbfgsM * D.npad));
+    TRY(h->dalloc(&D.Y, TL * kLbfgsM * D.npad));
+    TRY(h->dalloc(&D.R, TL * D.nb * D.Cp));
+    TRY(h->dalloc(&D.gpart, TL * D.G * D.npad));
+    TRY(h->dalloc(&D.spart, TL * D.G * kNumDots));
+    TRY(h->dalloc(&D.bar, TL * 32));
+    TRY(h->dalloc(&D.nfev, TL));
+    TRY(h->dalloc(&D.sum1, (size_t)D.npad + D.upad));
+    TRY(h->dalloc(&D.sum2, (size_t)D.E));
+    TRY(h->dalloc(&D.edge_stats, (size_t)D.E * 4));
+    TRY(h->dalloc(&D.leaf_xnorm, (size_t)D.C));
+    TRY(h->dalloc(&D.ctrl, 1));
+    const size_t cap = (size_t)std::max(1, h->admm_max_itr) * std::max(1, h->nodes_max_itr);
+    TRY(h->dalloc(&D.log_outer, cap));
+    TRY(h->dalloc(&D.log_itr, cap));
+    TRY(h->dalloc(&D.log_nfev, cap * TL));
+    TRY(h->dalloc(&D.log_pho, cap));
+    TRY(h->dalloc(&D.log_fold, cap));
+    TRY(h->dalloc(&D.log_primal, cap));
+    TRY(h->dalloc(&D.log_dual, cap));
+#undef TRY
+    SQW_CUDA_CHECK(cudaMallocHost((void **)&h->h_ring, sizeof(Ctrl) * kRing));
+    for (int i = 0; i < kRing; ++i) {
+        SQW_CUDA_CHECK(cudaEventCreate(&h->ev_x0[i]));
+        SQW_CUDA_CHECK(cudaEventCreate(&h->ev_x1[i]));
+        SQW_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_snap[i], cudaEventDisableTiming));
+    }
+    SQW_CUDA_CHECK(cudaEventCreate(&h->ev_a));
+    SQW_CUDA_CHECK(cudaEventCreate(&h->ev_b));
+    h->prepared = true;
+    return SQW_OK;
+}
+
+static int launch_xupdate(sqw_admm *h)
+{
+    AdmmDev &D = h->dev;
+    XKernel xk = xupdate_kernel(D.Cp / 8, h->xupdate_smem > 0);
+    void *args[] = {&D};
+    SQW_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)xk, dim3(D.T_local * D.G), dim3(kThreads),
+                                               args, h->xupdate_smem, h->stream));
+    return SQW_OK;
+}
+
+static int nccl_allreduce(sqw_admm *h, double *buf, size_t count)
+{
+    if (h->world <= 1)
+        return SQW_OK;
+    NcclApi *api = nccl_api();
+    int rc = api->AllReduce(buf, buf, count, kNcclDouble, kNcclSum, h->comm, h->stream);
+    if (rc != 0)
+        return set_error(SQW_ERR_NCCL, "ncclAllReduce failed: %s",
+                         api->GetErrorString ? api->GetErrorString(rc) : "?");
+    return SQW_OK;
+}
+
+// One ADMM iteration's worth of launches (LOne.java:608-716), no host synchronisation.
+static int enqueue_iteration(sqw_admm *h, int slot)
+{
+    AdmmDev &D = h->dev;
+    int rc;
+    SQW_CUDA_CHECK(cudaEventRecord(h->ev_x0[slot], h->stream));
+    if ((rc = launch_xupdate(h)) != SQW_OK)
+        return rc;
+    SQW_CUDA_CHECK(cudaEventRecord(h->ev_x1[slot], h->stream));
+    const int total = D.npad + D.upad;
+    admm_pack_kernel<<<(total + 255) / 256, 256, 0, h->stream>>>(D);
+    if ((rc = nccl_allreduce(h, D.sum1, (size_t)total)) != SQW_OK)
+        return rc;
+    admm_consensus_kernel<<<D.E, 256, 0, h->stream>>>(D);
+    if ((rc = nccl_allreduce(h, D.sum2, (size_t)D.E)) != SQW_OK)
+        return rc;
+    admm_decide_kernel<<<1, 32, 0, h->stream>>>(D);
+    SQW_CUDA_CHECK(cudaMemcpyAsync(&h->h_ring[slot], D.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost,
+                                   h->stream));
+    SQW_CUDA_CHECK(cudaEventRecord(h->ev_snap[slot], h->stream));
+    SQW_CUDA_CHECK(cudaGetLastError());
+    h->stats.launches += 4;
+    return SQW_OK;
+}
+
+}  // namespace sqw
+
+extern "C" {
+
+int sqw_admm_create(sqw_admm **out)
+{
+    int rc = require_device();
+    if (rc != SQW_OK)
+        return rc;
+    if (!out)
+        return set_error(SQW_ERR_INVALID_ARG, "null handle pointer");
+    sqw_admm *h = new sqw_admm();
+    SQW_CUDA_CHECK(cudaGetDevice(&h->device));
+    SQW_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    *out = h;
+    return SQW_OK;
+}
+
+void sqw_admm_destroy(sqw_admm *h)
+{
+    if (!h)
+        return;
+    cudaSetDevice(h->device);
+    if (h->stream)
+        cudaStreamSynchronize(h->stream);
+    if (h->comm && nccl_api() && nccl_api()->CommDestroy)
+        nccl_api()->CommDestroy(h->comm);
+    for (void *p : h->allocs)
+        cudaFree(p);
+    if (h->h_ring) {
+        cudaFreeHost(h->h_ring);
+        for (int i = 0; i < kRing; ++i) {
+            cudaEventDestroy(h->ev_x0[i]);
+            cudaEventDestroy(h->ev_x1[i]);
+            cudaEventDestroy(h->ev_snap[i]);
+        }
+        cudaEventDestroy(h->ev_a);
+        cudaEventDestroy(h->ev_b);
+    }
+    if (h->stream)
+        cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int sqw_admm_set_params(sqw_admm *h, double ridge, double pho, int32_t num_threads,
+                        int32_t admm_max_itr, int32_t nodes_max_itr, int32_t debug)
+{
+    if (!h)
+        return set_error(SQW_ERR_INVALID_ARG, "null handle");
+    if (h->have_problem)
+        return set_error(SQW_ERR_STATE, "set_params must precede set_problem (the row blocking depends on T)");
+    if (num_threads < 1 || admm_max_itr < 1 || nodes_max_itr < 1 || !(pho > 0.0))
+        return set_error(SQW_ERR_INVALID_ARG, "invalid parameters (threads=%d A=%d S=%d pho=%g)",
+                         num_threads, admm_max_itr, nodes_max_itr, pho);
+    h->ridge = ridge;
+    h->pho = pho;
+    h->T = num_threads;
+    h->admm_max_itr = admm_max_itr;
+    h->nodes_max_itr = nodes_max_itr;
+    h->debug = debug;
+    h->have_params = true;
+    return SQW_OK;
+}
+
+int sqw_admm_set_structure(sqw_admm *h, int32_t num_nodes, int32_t num_layers,
+                           const int32_t *node_index, const int32_t *is_leaf, const int32_t *layer,
+                           const int32_t *parent_ptr, const int32_t *parent_idx,
+                           const int32_t *child_ptr, const int32_t *child_idx)
+{
+    if (!h || num_nodes < 1 || num_layers < 1 || !node_index || !is_leaf || !layer || !parent_ptr ||
+        !child_ptr)
+        return set_error(SQW_ERR_INVALID_ARG, "invalid structure arguments");
+    if (h->prepared)
+        return set_error(SQW_ERR_STATE, "structure already in use");
+    const int NN = num_nodes;
+    // leaves must be 0..C-1 (they index x, Classifier.java:340,389)
+    int C = 0;
+    for (int e = 0; e < NN; ++e) {
+        if (node_index[e] < 0 || node_index[e] >= NN || layer[e] < 0 || layer[e] >= num_layers)
+            return set_error(SQW_ERR_INVALID_ARG, "design entry %d out of range", e);
+        if (is_leaf[e])
+            ++C;
+    }
+    std::vector<int> entry_of(NN, -1);
+    for (int e = 0; e < NN; ++e)
+        entry_of[node_index[e]] = e;
+    for (int c = 0; c < C; ++c)
+        if (entry_of[c] < 0 || !is_leaf[entry_of[c]])
+            return set_error(SQW_ERR_INVALID_ARG, "leaf indices must be 0..%d", C - 1);
+    h->NN = NN;
+    h->num_layers = num_layers;
+    h->C_struct = C;
+    h->edge_leaf.clear();
+    h->edge_par.clear();
+    h->leaf_edge_ptr.assign(C + 1, 0);
+    for (int c = 0; c < C; ++c) {
+        const int e = entry_of[c];
+        const int np = parent_ptr[e + 1] - parent_ptr[e];
+        if (np > kMaxEdgesPerLeaf)
+            return set_error(SQW_ERR_UNSUPPORTED, "leaf %d has %d parents (max %d)", c, np,
+                             kMaxEdgesPerLeaf);
+        if (np > 0) {
+            for (int k = parent_ptr[e]; k < parent_ptr[e + 1]; ++k) {
+                if (parent_idx[k] < 0 || parent_idx[k] >= NN)
+                    return set_error(SQW_ERR_INVALID_ARG, "parent index out of range");
+                h->edge_leaf.push_back(c);
+                h->edge_par.push_back(parent_idx[k]);
+            }
+        } else {  // self edge of a parentless leaf (LOne.java:440,697,846)
+            h->edge_leaf.push_back(c);
+            h->edge_par.push_back(-1);
+        }
+        h->leaf_edge_ptr[c + 1] = (int)h->edge_leaf.size();
+    }
+    const int E = (int)h->edge_leaf.size();
+    h->edge_sum_order.resize(E);
+    for (int i = 0; i < E; ++i)
+        h->edge_sum_order[i] = i;
+    std::stable_sort(h->edge_sum_order.begin(), h->edge_sum_order.end(), [&](int a, int b) {
+        const long long ka = (long long)h->edge_leaf[a] * NN + (h->edge_par[a] < 0 ? h->edge_leaf[a] : h->edge_par[a]);
+        const long long kb = (long long)h->edge_leaf[b] * NN + (h->edge_par[b] < 0 ? h->edge_leaf[b] : h->edge_par[b]);
+        return ka < kb;
+    });
+    // label layers in file order; neighbours = parents then children (LOne.java:229-234)
+    h->layers.assign(num_layers, sqw_admm::Layer());
+    for (int e = 0; e < NN; ++e) {
+        const int l = layer[e];
+        if (l == 0)
+            continue;
+        auto &L = h->layers[l];
+        if (L.nbr_ptr.empty())
+            L.nbr_ptr.push_back(0);
+        L.nodes.push_back(node_index[e]);
+        if (is_leaf[e])
+            for (int k = parent_ptr[e]; k < parent_ptr[e + 1]; ++k)
+                L.nbr_idx.push_back(parent_idx[k]);
+        else
+            for (int k = child_ptr[e]; k < child_ptr[e + 1]; ++k) {
+                if (child_idx[k] < 0 || child_idx[k] >= NN)
+                    return set_error(SQW_ERR_INVALID_ARG, "child index out of range");
+                L.nbr_idx.push_back(child_idx[k]);
+            }
+        if ((int)L.nbr_idx.size() - L.nbr_ptr.back() > kMaxFanIn)
+            return set_error(SQW_ERR_UNSUPPORTED, "node %d has more than %d neighbours",
+                             node_index[e], kMaxFanIn);
+        L.nbr_ptr.push_back((int)L.nbr_idx.size());
+    }
+    h->have_structure = true;
+    return SQW_OK;
+}
+
+int sqw_nccl_unique_id(uint8_t id_out[128])
+{
+    NcclApi *api = nccl_api();
+    if (!api)
+        return set_error(SQW_ERR_NCCL, "libnccl.so.2 could not be loaded: %s", dlerror());
+    NcclUid id;
+    int rc = api->GetUniqueId(&id);
+    if (rc != 0)
+        return set_error(SQW_ERR_NCCL, "ncclGetUniqueId failed (%d)", rc);
+    memcpy(id_out, id.internal, 128);
+    return SQW_OK;
+}
+
+int sqw_admm_set_comm(sqw_admm *h, int32_t rank, int32_t world, const uint8_t nccl_id[128])
+{
+    if (!h || world < 1 || rank < 0 || rank >= world)
+        return set_error(SQW_ERR_INVALID_ARG, "invalid rank/world");
+    if (h->have_problem)
+        return set_error(SQW_ERR_STATE, "set_comm must precede set_problem");
+    h->rank = rank;
+    h->world = world;
+    if (world == 1)
+        return SQW_OK;
+    NcclApi *api = nccl_api();
+    if (!api)
+        return set_error(SQW_ERR_NCCL, "libnccl.so.2 could not be loaded");
+    NcclUid id;
+    memcpy(id.internal, nccl_id, 128);
+    SQW_CUDA_CHECK(cudaSetDevice(h->device));
+    int rc = api->CommInitRank(&h->comm, world, id, rank);
+    if (rc != 0)
+        return set_error(SQW_ERR_NCCL, "ncclCommInitRank failed: %s",
+                         api->GetErrorString ? api->GetErrorString(rc) : "?");
+    return SQW_OK;
+}
+
+// Row blocking shared by both set_problem variants (LOne.java:337-357): block t holds rows
+// i = t + T*s, s < floor(N/T); the local blocks are those with t % world == rank, stored in the
+// order the reference sums the thread buffers.
+static int plan_blocks(sqw_admm *h, int64_t n_rows, int32_t dim, int32_t num_classes)
+{
+    if (!h || n_rows < 1 || dim < 2 || num_classes < 1)
+        return set_error(SQW_ERR_INVALID_ARG, "invalid problem sizes");
+    if (!h->have_params)
+        return set_error(SQW_ERR_STATE, "set_params must precede set_problem");
+    if (h->have_problem)
+        return set_error(SQW_ERR_STATE, "problem already set");
+    if (n_rows / h->T < 1)
+        return set_error(SQW_ERR_INVALID_ARG, "fewer rows (%lld) than ADMM blocks (%d)",
+                         (long long)n_rows, h->T);
+    if (n_rows / h->T > (1 << 30))
+        return set_error(SQW_ERR_UNSUPPORTED, "block too large");
+    h->n_rows = n_rows;
+    h->dim = dim;
+    h->C = num_classes;
+    h->block_ids.clear();
+    for (int t : java_thread_order(h->T))
+        if (t % h->world == h->rank)
+            h->block_ids.push_back(t);
+    if (h->block_ids.empty())
+        return set_error(SQW_ERR_INVALID_ARG, "rank %d owns no ADMM block (T=%d, world=%d)",
+                         h->rank, h->T, h->world);
+    AdmmDev &D = h->dev;
+    D.T = h->T;
+    D.T_local = (int)h->block_ids.size();
+    D.nb = (int)(n_rows / h->T);
+    D.dim = dim;
+    D.dimp = (dim + 15) / 16 * 16;
+    return SQW_OK;
+}
+
+int sqw_admm_set_problem(sqw_admm *h, int64_t n_rows, int32_t dim, int32_t num_classes,
+                         const double *data, const int32_t *y, const double *w)
+{
+    int rc = plan_blocks(h, n_rows, dim, num_classes);
+    if (rc != SQW_OK)
+        return rc;
+    if (!data || !y || !w)
+        return set_error(SQW_ERR_INVALID_ARG, "null buffer");
+    SQW_CUDA_CHECK(cudaSetDevice(h->device));
+    AdmmDev &D = h->dev;
+    const size_t rows = (size_t)D.T_local * D.nb;
+    double *dX = nullptr, *dw = nullptr;
+    int *dy = nullptr;
+    if ((rc = h->dalloc(&dX, rows * D.dimp, false)) != SQW_OK) return rc;
+    if ((rc = h->dalloc(&dy, rows, false)) != SQW_OK) return rc;
+    if ((rc = h->dalloc(&dw, rows, false)) != SQW_OK) return rc;
+    // stage one block at a time in pinned memory
+    double *stage = nullptr;
+    const size_t blk_elems = (size_t)D.nb * D.dimp;
+    SQW_CUDA_CHECK(cudaMallocHost((void **)&stage, blk_elems * sizeof(double)));
+    std::vector<int> ys(D.nb);
+    std::vector<double> ws(D.nb);
+    for (int b = 0; b < D.T_local; ++b) {
+        const int t = h->block_ids[b];
+        for (int s = 0; s < D.nb; ++s) {
+            const int64_t i = (int64_t)t + (int64_t)h->T * s;
+            if (y[i] < 0 || y[i] >= num_classes) {
+                cudaFreeHost(stage);
+                return set_error(SQW_ERR_INVALID_ARG, "class %d of row %lld out of range", y[i],
+                                 (long long)i);
+            }
+            double *dst = stage + (size_t)s * D.dimp;
+            memcpy(dst, data + i * dim, sizeof(double) * dim);
+            for (int j = dim; j < D.dimp; ++j)
+                dst[j] = 0.0;
+            ys[s] = y[i];
+            ws[s] = w[i];
+        }
+        cudaError_t e = cudaMemcpyAsync(dX + (size_t)b * blk_elems, stage, blk_elems * sizeof(double),
+                                        cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(dy + (size_t)b * D.nb, ys.data(), sizeof(int) * D.nb,
+                                cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(dw + (size_t)b * D.nb, ws.data(), sizeof(double) * D.nb,
+                                cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess)
+            e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) {
+            cudaFreeHost(stage);
+            return set_error(SQW_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e));
+        }
+    }
+    cudaFreeHost(stage);
+    D.X = dX;
+    D.y = dy;
+    D.w = dw;
+    h->have_problem = true;
+    return SQW_OK;
+}
+
+int sqw_admm_set_problem_dev(sqw_admm *h, int64_t n_rows, int32_t dim, int32_t num_classes,
+                             const double *d_data, const int32_t *d_y, const double *d_w)
+{
+    int rc = plan_blocks(h, n_rows, dim, num_classes);
+    if (rc != SQW_OK)
+        return rc;
+    if (!d_data || !d_y || !d_w)
+        return set_error(SQW_ERR_INVALID_ARG, "null buffer");
+    SQW_CUDA_CHECK(cudaSetDevice(h->device));
+    AdmmDev &D = h->dev;
+    const size_t rows = (size_t)D.T_local * D.nb;
+    double *dX = nullptr, *dw = nullptr;
+    int *dy = nullptr, *dbid = nullptr;
+    if ((rc = h->dalloc(&dX, rows * D.dimp, false)) != SQW_OK) return rc;
+    if ((rc = h->dalloc(&dy, rows, false)) != SQW_OK) return rc;
+    if ((rc = h->dalloc(&dw, rows, false)) != SQW_OK) return rc;
+    if ((rc = h->dalloc(&dbid, (size_t)D.T_local, false)) != SQW_OK) return rc;
+    SQW_CUDA_CHECK(cudaMemcpyAsync(dbid, h->block_ids.data(), sizeof(int) * D.T_local,
+                                   cudaMemcpyHostToDevice, h->stream));
+    const int grid = (int)std::min<size_t>(rows, 148 * 16);
+    admm_block_rows_kernel<<<grid, 256, 0, h->stream>>>(d_data, d_y, d_w, dim, h->T, dbid,
+                                                        D.T_local, D.nb, D.dimp, dX, dy, dw);
+    SQW_CUDA_CHECK(cudaGetLastError());
+    SQW_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    D.X = dX;
+    D.y = dy;
+    D.w = dw;
+    h->have_problem = true;
+    return SQW_OK;
+}
+
+// host <-> padded device layout helpers
+static int upload_padded(sqw_admm *h, const double *src, int rows, int dim, int dimp, double *dst)
+{
+    std::vector<double> tmp((size_t)rows * dimp, 0.0);
+    for (int r = 0; r < rows; ++r)
+        memcpy(&tmp[(size_t)r * dimp], src + (size_t)r * dim, sizeof(double) * dim);
+    SQW_CUDA_CHECK(cudaMemcpyAsync(dst, tmp.data(), tmp.size() * sizeof(double),
+                                   cudaMemcpyHostToDevice, h->stream));
+    SQW_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    return SQW_OK;
+}
+
+static int download_padded(sqw_admm *h, const double *src, int rows, int dim, int dimp, double *dst)
+{
+    std::vector<double> tmp((size_t)rows * dimp);
+    SQW_CUDA_CHECK(cudaMemcpyAsync(tmp.data(), src, tmp.size() * sizeof(double),
+                                   cudaMemcpyDeviceToHost, h->stream));
+    SQW_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    for (int r = 0; r < rows; ++r)
+        memcpy(dst + (size_t)r * dim, &tmp[(size_t)r * dimp], sizeof(double) * dim);
+    return SQW_OK;
+}
+
+int sqw_admm_execute(sqw_admm *h, double *x_inout, double *smx_inout)
+{
+    if (!h || !x_inout || !smx_inout)
+        return set_error(SQW_ERR_INVALID_ARG, "null argument");
+    SQW_CUDA_CHECK(cudaSetDevice(h->device));
+    int rc = prepare(h);
+    if (rc != SQW_OK)
+        return rc;
+    AdmmDev &D = h->dev;
+    cudaStream_t st = h->stream;
+
+    // LOne(xinit, sm_xinit, ...) + initUandZ (LOne.java:80-85,110-114)
+    if ((rc = upload_padded(h, x_inout, D.C, D.dim, D.dimp, D.xbar)) != SQW_OK) return rc;
+    if ((rc = upload_padded(h, smx_inout, D.NN, D.dim, D.dimp, D.smx)) != SQW_OK) return rc;
+    SQW_CUDA_CHECK(cudaMemsetAsync(D.z, 0, sizeof(double) * D.upad, st));
+    SQW_CUDA_CHECK(cudaMemsetAsync(D.zold, 0, sizeof(double) * D.upad, st));
+    SQW_CUDA_CHECK(cudaMemsetAsync(D.ubar, 0, sizeof(double) * D.upad, st));
+    SQW_CUDA_CHECK(cudaMemsetAsync(D.xt, 0, sizeof(double) * (size_t)D.T_local * D.Cp * D.dimp, st));
+    Ctrl c0;
+    memset(&c0, 0, sizeof c0);
+    c0.pho = h->pho;
+    c0.fold = 1.0;
+    c0.max_itr = h->admm_max_itr;
+    c0.log_cap = std::max(1, h->admm_max_itr) * std::max(1, h->nodes_max_itr);
+    SQW_CUDA_CHECK(cudaMemcpyAsync(D.ctrl, &c0, sizeof c0, cudaMemcpyHostToDevice, st));
+    SQW_CUDA_CHECK(cudaStreamSynchronize(st));
+
+    h->stats = sqw_admm_stats{};
+    h->admm_iters.clear();
+    double ms_admm = 0.0, ms_eval = 0.0;
+    cudaEvent_t ev_t0, ev_t1;
+    SQW_CUDA_CHECK(cudaEventCreate(&ev_t0));
+    SQW_CUDA_CHECK(cudaEventCreate(&ev_t1));
+    SQW_CUDA_CHECK(cudaEventRecord(ev_t0, st));
+    Ctrl last = c0;
+    bool converged = false;
+    int outer_done = 0;
+
+    for (int it = 0; it < h->nodes_max_itr; ++it) {
+        admm_begin_kernel<<<148, 256, 0, st>>>(D, it, 1);
+        h->stats.launches += 1;
+        SQW_CUDA_CHECK(cudaEventRecord(h->ev_a, st));
+        // ADMMrunner.execute (LOne.java:595-760)
+        int enq = 0, seen = 0;
+        bool done = false;
+        while (!done) {
+            if (enq - seen < kLookahead && enq < h->admm_max_itr + kLookahead) {
+                if ((rc = enqueue_iteration(h, enq % kRing)) != SQW_OK)
+                    return rc;
+                ++enq;
+                continue;
+            }
+            const int slot = seen % kRing;
+            SQW_CUDA_CHECK(cudaEventSynchronize(h->ev_snap[slot]));
+            float ms = 0.f;
+            SQW_CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev_x0[slot], h->ev_x1[slot]));
+            ms_eval += ms;
+            last = h->h_ring[slot];
+            ++seen;
+            if (last.done || last.fatal)
+                done = true;
+        }
+        // drain the speculative iterations (their kernels return at once)
+        while (seen < enq) {
+            SQW_CUDA_CHECK(cudaEventSynchronize(h->ev_snap[seen % kRing]));
+            ++seen;
+        }
+        SQW_CUDA_CHECK(cudaEventRecord(h->ev_b, st));
+        SQW_CUDA_CHECK(cudaEventSynchronize(h->ev_b));
+        float ms = 0.f;
+        SQW_CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev_a, h->ev_b));
+        ms_admm += ms;
+        h->admm_iters.push_back(last.itr);
+        h->stats.total_admm_iters += last.itr;
+        outer_done = it + 1;
+        if (last.fatal)
+            break;
+
+        // sm_x[leaf] <- x-bar; updateInternalNodes: odd layers first, then even (LOne.java:208-221)
+        admm_copy_leaves_kernel<<<(D.npad + 255) / 256, 256, 0, st>>>(D);
+        h->stats.launches += 1;
+        for (int pass = 0; pass < 2; ++pass)
+            for (int l = (pass == 0 ? 1 : 2); l < h->num_layers; l += 2) {
+                auto &L = h->layers[l];
+                if (L.nodes.empty())
+                    continue;
+                const long long work = (long long)L.nodes.size() * (D.dim - 1);
+                admm_update_layer_kernel<<<(int)std::min<long long>((work + 255) / 256, 148 * 8), 256,
+                                           0, st>>>(D, L.d_nodes, (int)L.nodes.size(), L.d_ptr,
+                                                    L.d_idx);
+                h->stats.launches += 1;
+            }
+        admm_outer_check_kernel<<<D.NN, 256, 0, st>>>(D);
+        h->stats.launches += 1;
+        Ctrl cc;
+        SQW_CUDA_CHECK(cudaMemcpyAsync(&h->h_ring[0], D.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+        SQW_CUDA_CHECK(cudaStreamSynchronize(st));
+        cc = h->h_ring[0];
+        last = cc;
+        // LOne.java:176-180
+        if (cc.num_pass == D.NN)
+            converged = true;
+        else if (cc.num_pass_relaxed == D.NN && it > h->nodes_max_itr / 2)
+            converged = true;
+        if (converged)
+            break;
+    }
+    SQW_CUDA_CHECK(cudaEventRecord(ev_t1, st));
+    SQW_CUDA_CHECK(cudaEventSynchronize(ev_t1));
+    float ms_total = 0.f;
+    SQW_CUDA_CHECK(cudaEventElapsedTime(&ms_total, ev_t0, ev_t1));
+    cudaEventDestroy(ev_t0);
+    cudaEventDestroy(ev_t1);
+
+    if ((rc = download_padded(h, D.xbar, D.C, D.dim, D.dimp, x_inout)) != SQW_OK) return rc;
+    if ((rc = download_padded(h, D.smx, D.NN, D.dim, D.dimp, smx_inout)) != SQW_OK) return rc;
+
+    // logs
+    const int rows = last.log_rows;
+    h->log_outer.resize(rows); h->log_itr.resize(rows);
+    h->log_pho.resize(rows); h->log_fold.resize(rows);
+    h->log_primal.resize(rows); h->log_dual.resize(rows);
+    h->log_nfev.resize((size_t)rows * D.T_local);
+    if (rows > 0) {
+        SQW_CUDA_CHECK(cudaMemcpy(h->log_outer.data(), D.log_outer, sizeof(int) * rows, cudaMemcpyDeviceToHost));
+        SQW_CUDA_CHECK(cudaMemcpy(h->log_itr.data(), D.log_itr, sizeof(int) * rows, cudaMemcpyDeviceToHost));
+        SQW_CUDA_CHECK(cudaMemcpy(h->log_pho.data(), D.log_pho, sizeof(double) * rows, cudaMemcpyDeviceToHost));
+        SQW_CUDA_CHECK(cudaMemcpy(h->log_fold.data(), D.log_fold, sizeof(double) * rows, cudaMemcpyDeviceToHost));
+        SQW_CUDA_CHECK(cudaMemcpy(h->log_primal.data(), D.log_primal, sizeof(double) * rows, cudaMemcpyDeviceToHost));
+        SQW_CUDA_CHECK(cudaMemcpy(h->log_dual.data(), D.log_dual, sizeof(double) * rows, cudaMemcpyDeviceToHost));
+        SQW_CUDA_CHECK(cudaMemcpy(h->log_nfev.data(), D.log_nfev, sizeof(int) * (size_t)rows * D.T_local, cudaMemcpyDeviceToHost));
+    }
+    h->stats.outer_iters = outer_done;
+    h->stats.converged = converged ? 1 : 0;
+    h->stats.ran_admm = last.ran_admm;
+    h->stats.total_evals = last.total_evals;
+    h->stats.final_pho = last.pho;
+    h->stats.final_fold = last.fold;
+    h->stats.seconds_admm = ms_admm * 1e-3;
+    h->stats.seconds_total = ms_total * 1e-3;
+    h->stats.seconds_eval = ms_eval * 1e-3;
+    // algorithmic bytes of one evaluation of one block, two passes over X_b:
+    const long long b_eval = 2ll * D.nb * D.dim * 8 + 2ll * D.nb * D.C * 8 + 12ll * D.nb +
+                             2ll * D.C * D.dim * 8;
+    h->stats.eval_bytes = last.total_evals * b_eval;
+    if (last.fatal)
+        return set_error(SQW_ERR_NUMERIC, "NaN/Inf met by the solver (the reference would have thrown, LBFGS.java:792-814)");
+    return SQW_OK;
+}
+
+int sqw_admm_get_stats(const sqw_admm *h, sqw_admm_stats *out)
+{
+    if (!h || !out)
+        return set_error(SQW_ERR_INVALID_ARG, "null argument");
+    *out = h->stats;
+    return SQW_OK;
+}
+
+int sqw_admm_get_log(const sqw_admm *h, int32_t cap, int32_t *rows_out, int32_t *outer,
+                     int32_t *itr, double *pho, double *fold, double *primal, double *dual,
+                     int32_t *nfev, int32_t *admm_iters_per_outer)
+{
+    if (!h || !rows_out)
+        return set_error(SQW_ERR_INVALID_ARG, "null argument");
+    const int rows = (int)h->log_itr.size();
+    *rows_out = rows;
+    const int n = std::min(rows, (int)cap);
+    const int TL = h->dev.T_local;
+    for (int r = 0; r < n; ++r) {
+        if (outer) outer[r] = h->log_outer[r];
+        if (itr) itr[r] = h->log_itr[r];
+        if (pho) pho[r] = h->log_pho[r];
+        if (fold) fold[r] = h->log_fold[r];
+        if (primal) primal[r] = h->log_primal[r];
+        if (dual) dual[r] = h->log_dual[r];
+        if (nfev)
+            for (int b = 0; b < TL; ++b)
+                nfev[(size_t)r * TL + b] = h->log_nfev[(size_t)r * TL + b];
+    }
+    if (admm_iters_per_outer)
+        for (size_t i = 0; i < h->admm_iters.size(); ++i)
+            admm_iters_per_outer[i] = h->admm_iters[i];
+    return SQW_OK;
+}
+
+int sqw_admm_eval(sqw_admm *h, const double *cx, const double *smx, double pho, double *f_out,
+                  double *g_out)
+{
+    if (!h || !cx || !smx || !f_out || !g_out)
+        return set_error(SQW_ERR_INVALID_ARG, "null argument");
+    SQW_CUDA_CHECK(cudaSetDevice(h->device));
+    int rc = prepare(h);
+    if (rc != SQW_OK)
+        return rc;
+    AdmmDev &D = h->dev;
+    cudaStream_t st = h->stream;
+    SQW_CUDA_CHECK(cudaMemsetAsync(D.xt, 0, sizeof(double) * (size_t)D.T_local * D.Cp * D.dimp, st));
+    SQW_CUDA_CHECK(cudaMemsetAsync(D.ut, 0, sizeof(double) * (size_t)D.T_local * D.upad, st));
+    SQW_CUDA_CHECK(cudaMemsetAsync(D.z, 0, sizeof(double) * D.upad, st));
+    SQW_CUDA_CHECK(cudaMemsetAsync(D.bar, 0, sizeof(unsigned) * 32 * D.T_local, st));
+    for (int b = 0; b < D.T_local; ++b)
+        if ((rc = upload_padded(h, cx + (size_t)b * D.C * D.dim, D.C, D.dim, D.dimp,
+                                D.xt + (size_t)b * D.Cp * D.dimp)) != SQW_OK)
+            return rc;
+    if ((rc = upload_padded(h, smx, D.NN, D.dim, D.dimp, D.smx)) != SQW_OK)
+        return rc;
+    double *d_f = nullptr;
+    SQW_CUDA_CHECK(cudaMalloc((void **)&d_f, sizeof(double) * D.T_local));
+    SQW_CUDA_CHECK(cudaMemsetAsync(d_f, 0, sizeof(double) * D.T_local, st));
+    EKernel ek = eval_kernel(D.Cp / 8, h->xupdate_smem > 0);
+    void *args[] = {&D, &pho, &d_f};
+    cudaError_t e = cudaLaunchCooperativeKernel((void *)ek, dim3(D.T_local * D.G), dim3(kThreads),
+                                                args, h->xupdate_smem, st);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        cudaFree(d_f);
+        return set_error(SQW_ERR_CUDA, "eval kernel failed: %s", cudaGetErrorString(e));
+    }
+    SQW_CUDA_CHECK(cudaMemcpy(f_out, d_f, sizeof(double) * D.T_local, cudaMemcpyDeviceToHost));
+    cudaFree(d_f);
+    for (int b = 0; b < D.T_local; ++b)
+        if ((rc = download_padded(h, D.g + (size_t)b * D.npad, D.C, D.dim, D.dimp,
+                                  g_out + (size_t)b * D.C * D.dim)) != SQW_OK)
+            return rc;
+    return SQW_OK;
+}
+
+int sqw_lbfgs_rosenbrock(int32_t n, double *x_inout, double eps, int32_t *nfev_out,
+                         int32_t *iters_out, int32_t *iflag_out)
+{
+    int rc = require_device();
+    if (rc != SQW_OK)
+        return rc;
+    if (n < 2 || (n & 1) || !x_inout)
+        return set_error(SQW_ERR_INVALID_ARG, "n must be even and >= 2");
+    const int G = std::max(1, std::min(8, n / 64));
+    double *buf = nullptr;
+    unsigned *bar = nullptr;
+    int *out = nullptr;
+    const size_t nv = (size_t)n;
+    const size_t total = nv * (5 + 2 * kLbfgsM) + (size_t)G * kNumDots;
+    SQW_CUDA_CHECK(cudaMalloc((void **)&buf, total * sizeof(double)));
+    SQW_CUDA_CHECK(cudaMemset(buf, 0, total * sizeof(double)));
+    SQW_CUDA_CHECK(cudaMalloc((void **)&bar, 128));
+    SQW_CUDA_CHECK(cudaMemset(bar, 0, 128));
+    SQW_CUDA_CHECK(cudaMalloc((void **)&out, 2 * sizeof(int)));
+    SolveWs ws;
+    ws.n = n;
+    ws.x = buf;
+    ws.g = buf + nv;
+    ws.gold = buf + 2 * nv;
+    ws.d = buf + 3 * nv;
+    ws.wa = buf + 4 * nv;
+    ws.S = buf + 5 * nv;
+    ws.Y = buf + (5 + kLbfgsM) * nv;
+    ws.spart = buf + (5 + 2 * kLbfgsM) * nv;
+    ws.G = G;
+    ws.cta = 0;
+    SQW_CUDA_CHECK(cudaMemcpy(ws.x, x_inout, nv * sizeof(double), cudaMemcpyHostToDevice));
+    void *args[] = {&ws, &bar, &eps, &out};
+    cudaError_t e = cudaLaunchCooperativeKernel((void *)lbfgs_rosenbrock_kernel, dim3(G),
+                                                dim3(kThreads), args, 0, 0);
+    if (e == cudaSuccess)
+        e = cudaDeviceSynchronize();
+    int res[2] = {0, 0};
+    if (e == cudaSuccess)
+        e = cudaMemcpy(res, out, sizeof res, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess)
+        e = cudaMemcpy(x_inout, ws.x, nv * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(buf);
+    cudaFree(bar);
+    cudaFree(out);
+    if (e != cudaSuccess)
+        return set_error(SQW_ERR_CUDA, "rosenbrock kernel failed: %s", cudaGetErrorString(e));
+    if (nfev_out) *nfev_out = res[0];
+    if (iters_out) *iters_out = 0;
+    if (iflag_out) *iflag_out = (res[1] == 0) ? 0 : (res[1] == 1 ? -1 : -100);
+    return SQW_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,457 @@
+// admm_kernels.cuh — the kernels of one consensus-ADMM iteration (path 2).
+//
+// Replaces framework/LOne.java: ADMMrun.run (:811-914, worker: u-update + L-BFGS x-update),
+// ADMMrunner.execute's consensus step (:670-716), updateResiduals / norms (:418-510),
+// updatePhoAndFold (:511-535), hasADMMConverged (:544-581), updateInternalNodes (:208-241) and
+// the outer convergence test (:149-180).
+//
+// Per ADMM iteration the host enqueues, with no synchronisation:
+//     admm_xupdate_kernel   cooperative, T_local groups of G CTAs, one group per ADMM block
+//     admm_pack_kernel      sum over local blocks of x_t | u_t        [ncclAllReduce if world>1]
+//     admm_consensus_kernel one CTA per (leaf,parent) edge: x-bar, u-bar, z-update, norms,
+//                           dual residual, local part of the primal residual
+//                                                                     [ncclAllReduce if world>1]
+//     admm_decide_kernel    residual bookkeeping, rho adaptation, convergence -> Ctrl.done
+// Once Ctrl.done is set the kernels of later (speculatively enqueued) iterations return at once.
+//
+// Reordering relative to the reference, results unchanged: hasADMMConverged(k-1) is evaluated
+// right after iteration k-1's residuals instead of after iteration k's x-update, because it
+// depends on nothing that x-update produces; the x-update whose result the reference computes and
+// then discards on convergence (LOne.java:649-665,753-758) is therefore never run. The rho update
+// of iteration k (:614-615) still precedes that test, as in the reference.
+#pragma once
+
+#include "admm_solver.cuh"
+
+namespace sqw {
+
+__device__ __forceinline__ int ld_volatile_int(const int *p)
+{
+    return *reinterpret_cast<const volatile int *>(p);
+}
+
+// ------------------------------------------------------------------ x-update
+template <int NCT, bool W_SMEM>
+struct BlockProblem {
+    const AdmmDev &P;
+    int blk, cta;
+    double *smW;
+    double *red;
+    double pho;
+    const double *ut;
+
+    __device__ double eval_partial(const double *x)
+    {
+        return eval_data_term<NCT, W_SMEM>(P, blk, cta, x, smW, red);
+    }
+
+    // gradient of coordinate k: data term reduced over the group's partials, plus the augmented
+    // Lagrangian term rho*(x - sm_x[par] - z + u_t) for w >= 1 (LOne.java:982-998); faug
+    // accumulates rho/2 * (...)^2 (LOne.java:1031-1047).
+    __device__ double grad_coord(int k, const double *x, double &faug)
+    {
+        const double *gp = P.gpart + (size_t)blk * P.G * P.npad + k;
+        double s = 0.0;
+        for (int c = 0; c < P.G; ++c)
+            s += __ldcg(gp + (size_t)c * P.npad);
+        const int leaf = k / P.dimp, w = k - leaf * P.dimp;
+        if (w >= 1 && w < P.dim) {
+            const double xk = __ldcg(x + k);
+            for (int e = P.leaf_edge_ptr[leaf]; e < P.leaf_edge_ptr[leaf + 1]; ++e) {
+                const int par = P.edge_par[e];
+                const size_t o = (size_t)e * P.dimp + w;
+                double v = xk;
+                if (par >= 0)
+                    v -= P.smx[(size_t)par * P.dimp + w];
+                v = (v - P.z[o]) + __ldcg(ut + o);
+                s += pho * v;
+                faug += (pho / 2) * v * v;
+            }
+        }
+        return s;
+    }
+};
+
+template <int NCT, bool W_SMEM>
+__global__ void __launch_bounds__(kThreads, 1) admm_xupdate_kernel(AdmmDev P)
+{
+    extern __shared__ __align__(16) double smW[];
+    __shared__ SolveSmem sm;
+    if (ld_volatile_int(&P.ctrl->done) || ld_volatile_int(&P.ctrl->fatal))
+        return;
+    const int blk = blockIdx.x / P.G, cta = blockIdx.x - blk * P.G;
+    const double pho = P.ctrl->pho, fold = P.ctrl->fold;
+    double *xt = P.xt + (size_t)blk * P.Cp * P.dimp;
+    double *ut = P.ut + (size_t)blk * P.upad;
+
+    // u-update (LOne.java:833-861): x-hat_t = a x_t + (1-a) z_old - a sm_x[par];
+    // u_t += x-hat_t - z; u_t /= rho_fold.  Slice of the edge coordinates per CTA.
+    {
+        const int usl = ((P.upad + P.G - 1) / P.G + 15) & ~15;
+        const int u0 = min(P.upad, cta * usl), u1 = min(P.upad, u0 + usl);
+        for (int i = u0 + threadIdx.x; i < u1; i += kThreads) {
+            const int e = i / P.dimp, w = i - e * P.dimp;
+            if (w >= P.dim)
+                continue;
+            const int leaf = P.edge_leaf[e], par = P.edge_par[e];
+            double xhat = kAlpha * xt[(size_t)leaf * P.dimp + w] + (1 - kAlpha) * P.zold[i];
+            if (par >= 0)
+                xhat -= kAlpha * P.smx[(size_t)par * P.dimp + w];
+            double u = ut[i] + xhat - P.z[i];
+            ut[i] = u / fold;
+        }
+    }
+
+    GroupBarrier gb{P.bar + blk * 32, 0u, P.G};
+    BlockProblem<NCT, W_SMEM> prob{P, blk, cta, smW, sm.red, pho, ut};
+    SolveWs ws;
+    ws.n = P.npad;
+    ws.x = xt;
+    ws.g = P.g + (size_t)blk * P.npad;
+    ws.gold = P.gold + (size_t)blk * P.npad;
+    ws.d = P.d + (size_t)blk * P.npad;
+    ws.wa = P.wa + (size_t)blk * P.npad;
+    ws.S = P.S + (size_t)blk * kLbfgsM * P.npad;
+    ws.Y = P.Y + (size_t)blk * kLbfgsM * P.npad;
+    ws.spart = P.spart + (size_t)blk * P.G * kNumDots;
+    ws.G = P.G;
+    ws.cta = cta;
+    int status = 0;
+    const int evals = lbfgs_group_solve(prob, ws, gb, sm, 0.1, 10e-16, status);  // LOne.java:874-875
+    if (cta == 0 && threadIdx.x == 0) {
+        P.nfev[blk] = evals;
+        if (status == 1)
+            atomicAdd(&P.ctrl->lbfgs_errors, 1);
+        if (status == 2)
+            atomicExch(&P.ctrl->fatal, 1);
+    }
+}
+
+// ------------------------------------------------------------------ pack: sum over local blocks
+__global__ void __launch_bounds__(256) admm_pack_kernel(AdmmDev P)
+{
+    if (ld_volatile_int(&P.ctrl->done) || ld_volatile_int(&P.ctrl->fatal))
+        return;
+    const int total = P.npad + P.upad;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        double s = 0.0;
+        if (i < P.npad) {
+            for (int b = 0; b < P.T_local; ++b)  // local blocks are stored in summation order
+                s += P.xt[(size_t)b * P.Cp * P.dimp + i];
+        } else {
+            for (int b = 0; b < P.T_local; ++b)
+                s += P.ut[(size_t)b * P.upad + (i - P.npad)];
+        }
+        P.sum1[i] = s;
+    }
+}
+
+// ------------------------------------------------------------------ consensus, one CTA per edge
+// LOne.java:670-716 restricted to edge e = (leaf, par): z_old <- z, x-bar, u-bar, x-hat, z,
+// soft-threshold with kappa = 2 lambda / (rho T) (intercept included), znorm (from u for a self
+// edge, :504), xnorm, dual residual term, and this rank's part of the primal residual term.
+__global__ void __launch_bounds__(256) admm_consensus_kernel(AdmmDev P)
+{
+    __shared__ double red[kWarps];
+    if (ld_volatile_int(&P.ctrl->done) || ld_volatile_int(&P.ctrl->fatal))
+        return;
+    const int e = blockIdx.x;
+    const int leaf = P.edge_leaf[e], par = P.edge_par[e];
+    const bool first_edge = (P.leaf_edge_ptr[leaf] == e);
+    const double pho = P.ctrl->pho;
+    const double kappa = (2 * P.ridge) / (pho * P.T);
+    const double Td = (double)P.T;
+    double zn2 = 0, du2 = 0, xn2 = 0, pr2 = 0, cn2 = 0;
+    for (int w = threadIdx.x; w < P.dim; w += blockDim.x) {
+        const size_t o = (size_t)e * P.dimp + w, xo = (size_t)leaf * P.dimp + w;
+        const double xb = P.sum1[xo] / Td;
+        const double ub = P.sum1[P.npad + o] / Td;
+        const double zo = P.z[o];
+        double smp = 0.0;
+        double xhat = kAlpha * xb + (1 - kAlpha) * zo;
+        if (par >= 0) {
+            smp = P.smx[(size_t)par * P.dimp + w];
+            xhat -= kAlpha * smp;
+            cn2 += smp * smp;
+        }
+        double zn = xhat + ub;
+        const double sg = (zn > 0.0) ? 1.0 : ((zn < 0.0) ? -1.0 : zn);
+        zn = zn - sg * fmin(kappa, fabs(zn));
+        P.zold[o] = zo;
+        P.z[o] = zn;
+        P.ubar[o] = ub;
+        if (first_edge) {
+            P.xbar[xo] = xb;
+            xn2 += xb * xb;
+        }
+        zn2 += (par >= 0) ? zn * zn : ub * ub;
+        const double dd = pho * (zn - zo);
+        du2 += dd * dd;
+        for (int b = 0; b < P.T_local; ++b) {
+            const double r = P.xt[(size_t)b * P.Cp * P.dimp + xo] - zn - smp;
+            pr2 += r * r;
+        }
+    }
+    zn2 = block_sum(zn2, red);
+    du2 = block_sum(du2, red);
+    xn2 = block_sum(xn2, red);
+    pr2 = block_sum(pr2, red);
+    cn2 = block_sum(cn2, red);
+    if (threadIdx.x == 0) {
+        P.edge_stats[e * 4 + 0] = zn2;
+        P.edge_stats[e * 4 + 1] = du2;
+        P.edge_stats[e * 4 + 2] = cn2;
+        P.sum2[e] = pr2;
+        if (first_edge)
+            P.leaf_xnorm[leaf] = xn2;
+    }
+}
+
+// ------------------------------------------------------------------ decide (one thread)
+__global__ void admm_decide_kernel(AdmmDev P)
+{
+    Ctrl *c = P.ctrl;
+    if (threadIdx.x != 0 || blockIdx.x != 0)
+        return;
+    if (c->done || c->fatal)
+        return;
+    // updateResiduals (LOne.java:418-454): the accumulators run on across a leaf's parents and
+    // the dual one is square-rooted in place.
+    double primal[kMaxEdgesPerLeaf], dual[kMaxEdgesPerLeaf];
+    bool converged = true;
+    const double abs_tol = sqrt((double)P.dim) * kAbsTol;
+    const double rel = sqrt((double)P.T) * kRelTol;
+    for (int leaf = 0; leaf < P.C; ++leaf) {
+        double r_t = 0.0, s_t = 0.0;
+        const int e0 = P.leaf_edge_ptr[leaf], e1 = P.leaf_edge_ptr[leaf + 1];
+        const double xnorm = sqrt(P.leaf_xnorm[leaf]);
+        for (int e = e0; e < e1; ++e) {
+            r_t += P.sum2[e];
+            s_t += P.edge_stats[e * 4 + 1];
+            s_t = sqrt(s_t * P.T);
+            primal[e - e0] = sqrt(r_t);
+            dual[e - e0] = s_t;
+            P.edge_stats[e * 4 + 3] = primal[e - e0];
+            P.edge_stats[e * 4 + 1] = dual[e - e0];
+            // hasADMMConverged (LOne.java:544-581); unorm is always 0 when read (:650 vs :680)
+            const double znorm = sqrt(P.edge_stats[e * 4 + 0]);
+            const double cnorm = sqrt(P.edge_stats[e * 4 + 2]);
+            const double mx = (P.edge_par[e] >= 0) ? fmax(xnorm, fmax(znorm, cnorm))
+                                                   : fmax(xnorm, znorm);
+            const double primal_tol = abs_tol + rel * mx;
+            const double dual_tol = abs_tol + rel * c->pho * 0.0;
+            if (primal[e - e0] > primal_tol || dual[e - e0] > dual_tol)
+                converged = false;
+        }
+    }
+    double ps = 0.0, ds = 0.0;  // LOne.java:519-522 sums, in i = leaf*NN+pid order
+    for (int i = 0; i < P.E; ++i) {
+        const int e = P.edge_sum_order[i];
+        ps += P.edge_stats[e * 4 + 3];
+        ds += P.edge_stats[e * 4 + 1];
+    }
+    if (c->log_rows < c->log_cap) {
+        const int r = c->log_rows++;
+        P.log_outer[r] = c->outer;
+        P.log_itr[r] = c->itr;
+        P.log_pho[r] = c->pho;
+        P.log_fold[r] = c->fold;
+        P.log_primal[r] = ps;
+        P.log_dual[r] = ds;
+        for (int b = 0; b < P.T_local; ++b)
+            P.log_nfev[(size_t)r * P.T_local + b] = P.nfev[b];
+    }
+    for (int b = 0; b < P.T_local; ++b) {
+        c->total_evals += P.nfev[b];
+        P.bar[b * 32] = 0u;
+    }
+    c->itr += 1;
+    if (c->itr < c->max_itr) {
+        // top of the next loop trip: updatePhoAndFold(itr-1) (LOne.java:511-535,614-615) ...
+        if (!c->ran_admm && c->pho < kPhoMax) {
+            const double mu = 10, tao = 2;
+            if (ps > mu * ds) {
+                const double old = c->pho;
+                c->pho = fmin(kPhoMax, c->pho * tao);
+                c->fold = c->pho / old;
+            } else if (ds > ps * mu) {
+                c->pho = c->pho / tao;
+                c->fold = 1 / tao;
+            } else {
+                c->fold = 1.0;
+            }
+        }
+        // ... then hasADMMConverged(itr-1) (:649-665)
+        if (converged) {
+            c->ran_admm = 1;
+            c->done = 1;
+        }
+    } else {
+        c->done = 1;
+    }
+}
+
+// ------------------------------------------------------------------ outer-iteration kernels
+// new ADMMrunner() (LOne.java:360-391): t_x <- x, t_u <- u; iteration counter reset.
+__global__ void __launch_bounds__(256) admm_begin_kernel(AdmmDev P, int outer, int snapshot)
+{
+    const int stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int i = tid; i < P.npad; i += stride)
+        for (int b = 0; b < P.T_local; ++b)
+            P.xt[(size_t)b * P.Cp * P.dimp + i] = P.xbar[i];
+    for (int i = tid; i < P.upad; i += stride)
+        for (int b = 0; b < P.T_local; ++b)
+            P.ut[(size_t)b * P.upad + i] = P.ubar[i];
+    if (snapshot)  // sm_x_old (LOne.java:122-126)
+        for (int i = tid; i < P.NN * P.dimp; i += stride)
+            P.smx_old[i] = P.smx[i];
+    if (tid == 0) {
+        P.ctrl->itr = 0;
+        P.ctrl->done = 0;
+        P.ctrl->outer = outer;
+        P.ctrl->num_pass = 0;
+        P.ctrl->num_pass_relaxed = 0;
+        for (int b = 0; b < P.T_local; ++b) {
+            P.bar[b * 32] = 0u;
+            P.nfev[b] = 0;
+        }
+    }
+}
+
+// sm_x[leaf] <- x-bar (LOne.java:753-758)
+__global__ void __launch_bounds__(256) admm_copy_leaves_kernel(AdmmDev P)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.npad; i += gridDim.x * blockDim.x)
+        P.smx[i] = P.xbar[i];
+}
+
+// updateNode (LOne.java:223-241) for the nodes of one layer: lower median over parents' and
+// children's weights, intercept untouched. One thread per (node, w).
+__global__ void __launch_bounds__(256)
+admm_update_layer_kernel(AdmmDev P, const int *nodes, int n_nodes, const int *nbr_ptr,
+                         const int *nbr_idx)
+{
+    const int per = P.dim - 1;
+    const long long total = (long long)n_nodes * per;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int ni = (int)(i / per), w = (int)(i - (long long)ni * per) + 1;
+        const int node = nodes[ni];
+        const int b = nbr_ptr[ni], cnt = nbr_ptr[ni + 1] - b;
+        if (cnt <= 0)
+            continue;  // xs.get(-1) would throw in the reference; never happens for its designs
+        double xs[kMaxFanIn];
+        for (int j = 0; j < cnt; ++j) {  // insertion sort (Collections.sort, ascending)
+            const double v = P.smx[(size_t)nbr_idx[b + j] * P.dimp + w];
+            int q = j;
+            while (q > 0 && xs[q - 1] > v) {
+                xs[q] = xs[q - 1];
+                --q;
+            }
+            xs[q] = v;
+        }
+        P.smx[(size_t)node * P.dimp + w] = (cnt % 2 == 0) ? xs[cnt / 2 - 1] : xs[cnt / 2];
+    }
+}
+
+// LOne.java:152-174: per node delta = ||sm_x_old - sm_x||, target = NODES_tol * ||sm_x||.
+__global__ void __launch_bounds__(256) admm_outer_check_kernel(AdmmDev P)
+{
+    __shared__ double red[kWarps];
+    const int node = blockIdx.x;
+    double d2 = 0, n2 = 0;
+    for (int w = threadIdx.x; w < P.dim; w += blockDim.x) {
+        const size_t o = (size_t)node * P.dimp + w;
+        const double a = P.smx[o], df = P.smx_old[o] - a;
+        d2 += df * df;
+        n2 += a * a;
+    }
+    d2 = block_sum(d2, red);
+    n2 = block_sum(n2, red);
+    if (threadIdx.x == 0) {
+        const double delta = sqrt(d2), target = kNodesTol * sqrt(n2);
+        if (delta < target)
+            atomicAdd(&P.ctrl->num_pass, 1);
+        if (delta < target * 2 / kNodesTol)
+            atomicAdd(&P.ctrl->num_pass_relaxed, 1);
+    }
+}
+
+// Gather rows into the block-major padded layout (LOne.java:337-357): local block b holds rows
+// i = t + T*s of the caller's row-major matrix, t = block_ids[b].
+__global__ void __launch_bounds__(256)
+admm_block_rows_kernel(const double *src, const int *ysrc, const double *wsrc, int dim, int T,
+                       const int *block_ids, int T_local, int nb, int dimp, double *X, int *y,
+                       double *w)
+{
+    const long long rows = (long long)T_local * nb;
+    for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+        const int b = (int)(r / nb), s = (int)(r - (long long)b * nb);
+        const long long i = (long long)block_ids[b] + (long long)T * s;
+        const double *in = src + i * dim;
+        double *out = X + r * dimp;
+        for (int j = threadIdx.x; j < dimp; j += blockDim.x)
+            out[j] = (j < dim) ? in[j] : 0.0;
+        if (threadIdx.x == 0) {
+            y[r] = ysrc[i];
+            w[r] = wsrc[i];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ test kernels
+// One evaluation per local block at the current x_t with the device's z / u_t / sm_x state.
+template <int NCT, bool W_SMEM>
+__global__ void __launch_bounds__(kThreads, 1) admm_eval_kernel(AdmmDev P, double pho, double *f_out)
+{
+    extern __shared__ __align__(16) double smW[];
+    __shared__ SolveSmem sm;
+    const int blk = blockIdx.x / P.G, cta = blockIdx.x - blk * P.G;
+    double *xt = P.xt + (size_t)blk * P.Cp * P.dimp;
+    GroupBarrier gb{P.bar + blk * 32, 0u, P.G};
+    BlockProblem<NCT, W_SMEM> prob{P, blk, cta, smW, sm.red, pho, P.ut + (size_t)blk * P.upad};
+    const double fpart = prob.eval_partial(xt);
+    gb.sync();
+    const int n = P.npad;
+    const int sl = ((n + P.G - 1) / P.G + 15) & ~15;
+    const int k0 = min(n, cta * sl), k1 = min(n, k0 + sl);
+    double faug = 0.0;
+    for (int k = k0 + threadIdx.x; k < k1; k += kThreads)
+        P.g[(size_t)blk * n + k] = prob.grad_coord(k, xt, faug);
+    const double fa = block_sum(faug, sm.red);
+    if (threadIdx.x == 0)
+        atomicAdd(f_out + blk, fpart + fa);
+}
+
+struct RosenProblem {
+    int n;
+    __device__ double eval_partial(const double *) { return 0.0; }
+    __device__ double grad_coord(int k, const double *x, double &facc)
+    {
+        const int i = k >> 1;
+        const double a = __ldcg(x + 2 * i), b = __ldcg(x + 2 * i + 1);
+        const double t1 = b - a * a;
+        if ((k & 1) == 0) {
+            facc += 100.0 * t1 * t1 + (1.0 - a) * (1.0 - a);
+            return -400.0 * a * t1 - 2.0 * (1.0 - a);
+        }
+        return 200.0 * t1;
+    }
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+lbfgs_rosenbrock_kernel(SolveWs ws, unsigned *bar, double eps, int *out)
+{
+    __shared__ SolveSmem sm;
+    RosenProblem prob{ws.n};
+    ws.cta = blockIdx.x;
+    GroupBarrier gb{bar, 0u, ws.G};
+    int status = 0;
+    const int evals = lbfgs_group_solve(prob, ws, gb, sm, eps, 10e-16, status);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        out[0] = evals;
+        out[1] = status;
+    }
+}
+
+}  // namespace sqw

@@ -1,0 +1,294 @@
+"""Host-side mirror of the reference's trainer plug-in API.
+
+``Optimizer`` restates the abstract class framework/Optimizer.java:5-27 (same method names and
+argument meaning); ``LOneCuda`` is the B200 implementation that takes the place of
+framework/LOne.java behind it: ``Classifier.buildClassifier`` constructs it, pushes the setters in
+the order of framework/Classifier.java:422-443, calls ``execute()`` and pulls ``getX()`` /
+``getsmX()`` (:444-449). All compute goes through the C ABI (``sqw_admm_*``); there is no CPU
+path. Citations are relative to /root/reference/src/org/seqcode/projects/sequnwinder/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from abc import ABC, abstractmethod
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+
+from . import _lib
+from .structure import ClassRelationStructure
+
+
+class Optimizer(ABC):
+    """framework/Optimizer.java:5-27"""
+
+    @abstractmethod
+    def setBGFSmaxItrs(self, m: int): ...
+
+    @abstractmethod
+    def setSeqUnwinderMaxIts(self, m: int): ...
+
+    @abstractmethod
+    def setInstanceWeights(self, w): ...
+
+    @abstractmethod
+    def setClsMembership(self, c): ...
+
+    @abstractmethod
+    def setNumPredictors(self, p: int): ...
+
+    @abstractmethod
+    def setNumClasses(self, c: int): ...
+
+    @abstractmethod
+    def setClassStructure(self, rel: ClassRelationStructure): ...
+
+    @abstractmethod
+    def setNumNodes(self, n: int): ...
+
+    @abstractmethod
+    def setRidge(self, r: float): ...
+
+    @abstractmethod
+    def setDebugMode(self, debug: bool): ...
+
+    @abstractmethod
+    def execute(self): ...
+
+    @abstractmethod
+    def getX(self): ...
+
+    @abstractmethod
+    def getsmX(self): ...
+
+    @abstractmethod
+    def clearOptimizer(self): ...
+
+
+@dataclass
+class AdmmLog:
+    outer: np.ndarray
+    itr: np.ndarray
+    pho: np.ndarray
+    fold: np.ndarray
+    primal: np.ndarray
+    dual: np.ndarray
+    nfev: np.ndarray          # [rows, local blocks]
+    admm_iters: List[int]     # ADMM_currItr_value at exit, per outer iteration
+
+
+class LOneCuda(Optimizer):
+    """Drop-in for ``new LOne(xinit, sm_xinit, data)`` (LOne.java:110-114).
+
+    ``x`` (numClasses*dim, class-major, intercept first) and ``sm_x`` (numNodes*dim) are the
+    caller's arrays and receive the trained values in place, as in the reference;
+    ``data`` is the standardised n x dim matrix with column 0 == 1 (Classifier.java:337-381).
+    """
+
+    def __init__(self, xinit: np.ndarray, sm_xinit: np.ndarray, data: np.ndarray):
+        self.x = xinit
+        self.sm_x = sm_xinit
+        self.data = data
+        # LOne.java:24-51 defaults
+        self.ADMM_maxItr = 500
+        self.ADMM_pho = 1.7
+        self.ADMM_numThreads = 5
+        self.BGFS_maxIts = -1
+        self.NODES_maxItr = 10
+        self.regularization = 0.0
+        self.numPredictors = None
+        self.numClasses = None
+        self.numNodes = None
+        self.classStructure: Optional[ClassRelationStructure] = None
+        self.weights = None
+        self.cls = None
+        self.sm_Debug = False
+        self._rank, self._world, self._nccl_id = 0, 1, None
+        self._handle = None
+        self.stats: Optional[_lib.AdmmStats] = None
+        self.log: Optional[AdmmLog] = None
+        self._local_blocks = 0
+
+    # ---- setters, LOne.java:92-104 ----
+    def setBGFSmaxItrs(self, m): self.BGFS_maxIts = int(m)
+    def setADMMmaxItrs(self, m): self.ADMM_maxItr = int(m)
+    def setSeqUnwinderMaxIts(self, m): self.NODES_maxItr = int(m)
+    def setInstanceWeights(self, w): self.weights = w
+    def setClsMembership(self, c): self.cls = c
+    def setNumPredictors(self, p): self.numPredictors = int(p)
+    def setNumClasses(self, c): self.numClasses = int(c)
+
+    def setClassStructure(self, rel):
+        self.classStructure = rel
+        self.setNumNodes(rel.numNodes)
+
+    def setNumNodes(self, n): self.numNodes = int(n)
+    def setRidge(self, r): self.regularization = float(r)
+    def setDebugMode(self, debug): self.sm_Debug = bool(debug)
+    def setPho(self, ph): self.ADMM_pho = float(ph)
+    def set_numThreads(self, nt): self.ADMM_numThreads = int(nt)
+
+    def initUandZ(self):
+        """z, zold, u start at zero (LOne.java:80-85); allocated on the device by execute()."""
+
+    # ---- multi-GPU placement (no reference counterpart: T stays the numerics knob) ----
+    def setComm(self, rank: int, world: int, nccl_id: Optional[bytes]):
+        """Blocks t with t % world == rank are solved on this process's GPU; the consensus sums
+        (LOne.java:395-417) become ncclAllReduce. ``nccl_id``: 128 bytes from
+        ``nccl_unique_id()`` on rank 0, distributed by the caller."""
+        self._rank, self._world, self._nccl_id = int(rank), int(world), nccl_id
+
+    # ---- execute / getters ----
+    def execute(self):
+        lib = _lib.load()
+        if self.classStructure is None or self.cls is None or self.weights is None:
+            raise RuntimeError("setClassStructure / setClsMembership / setInstanceWeights first")
+        data = np.ascontiguousarray(self.data, dtype=np.float64)
+        n_rows, dim = data.shape
+        C_ = self.numClasses if self.numClasses is not None else int(np.max(self.cls)) + 1
+        if self.numPredictors is not None and self.numPredictors + 1 != dim:
+            raise ValueError("data has %d columns but numPredictors+1 = %d"
+                             % (dim, self.numPredictors + 1))
+        cls = np.ascontiguousarray(self.cls, dtype=np.int32)
+        w = np.ascontiguousarray(self.weights, dtype=np.float64)
+        st = self.classStructure.to_arrays()
+        NN = st["num_nodes"]
+        if self.x.size != C_ * dim or self.sm_x.size != NN * dim:
+            raise ValueError("x / sm_x have the wrong length")
+
+        def ip(a):
+            a = np.ascontiguousarray(a, dtype=np.int32)
+            if a.size == 0:
+                a = np.zeros(1, dtype=np.int32)
+            return a
+
+        arrs = {k: ip(st[k]) for k in ("node_index", "is_leaf", "layer", "parent_ptr",
+                                       "parent_idx", "child_ptr", "child_idx")}
+        h = C.c_void_p()
+        _lib.check(lib.sqw_admm_create(C.byref(h)))
+        self._handle = h
+        try:
+            _lib.check(lib.sqw_admm_set_structure(
+                h, NN, st["num_layers"], *[arrs[k].ctypes.data_as(_lib.i32p) for k in
+                                           ("node_index", "is_leaf", "layer", "parent_ptr",
+                                            "parent_idx", "child_ptr", "child_idx")]))
+            _lib.check(lib.sqw_admm_set_params(h, self.regularization, self.ADMM_pho,
+                                               self.ADMM_numThreads, self.ADMM_maxItr,
+                                               self.NODES_maxItr, int(self.sm_Debug)))
+            if self._world > 1:
+                idbuf = (C.c_uint8 * 128).from_buffer_copy(self._nccl_id)
+                _lib.check(lib.sqw_admm_set_comm(h, self._rank, self._world, idbuf))
+            _lib.check(lib.sqw_admm_set_problem(
+                h, n_rows, dim, C_, data.ctypes.data_as(_lib.f64p), cls.ctypes.data_as(_lib.i32p),
+                w.ctypes.data_as(_lib.f64p)))
+            x = np.ascontiguousarray(self.x, dtype=np.float64)
+            smx = np.ascontiguousarray(self.sm_x, dtype=np.float64)
+            rc = lib.sqw_admm_execute(h, x.ctypes.data_as(_lib.f64p), smx.ctypes.data_as(_lib.f64p))
+            self._collect(lib, h)
+            _lib.check(rc)
+            # results are returned through the caller's arrays, as LOne mutates x / sm_x in place
+            if x is not self.x:
+                np.copyto(self.x, x.reshape(self.x.shape))
+            if smx is not self.sm_x:
+                np.copyto(self.sm_x, smx.reshape(self.sm_x.shape))
+        finally:
+            lib.sqw_admm_destroy(h)
+            self._handle = None
+
+    def _collect(self, lib, h):
+        stats = _lib.AdmmStats()
+        _lib.check(lib.sqw_admm_get_stats(h, C.byref(stats)))
+        self.stats = stats
+        rows = C.c_int32(0)
+        _lib.check(lib.sqw_admm_get_log(h, 0, C.byref(rows), None, None, None, None, None, None,
+                                        None, None))
+        r = rows.value
+        T = self.ADMM_numThreads
+        tl = len([t for t in range(T) if t % self._world == self._rank])
+        self._local_blocks = tl
+        lo, li = np.zeros(max(r, 1), np.int32), np.zeros(max(r, 1), np.int32)
+        lp, lf, lpr, ld = (np.zeros(max(r, 1)) for _ in range(4))
+        ln = np.zeros((max(r, 1), tl), np.int32)
+        ai = np.zeros(max(1, self.NODES_maxItr), np.int32)
+        _lib.check(lib.sqw_admm_get_log(
+            h, r, C.byref(rows), lo.ctypes.data_as(_lib.i32p), li.ctypes.data_as(_lib.i32p),
+            lp.ctypes.data_as(_lib.f64p), lf.ctypes.data_as(_lib.f64p),
+            lpr.ctypes.data_as(_lib.f64p), ld.ctypes.data_as(_lib.f64p),
+            ln.ctypes.data_as(_lib.i32p), ai.ctypes.data_as(_lib.i32p)))
+        self.log = AdmmLog(lo[:r], li[:r], lp[:r], lf[:r], lpr[:r], ld[:r], ln[:r],
+                           [int(v) for v in ai[:stats.outer_iters]])
+
+    def getX(self): return self.x
+    def getsmX(self): return self.sm_x
+
+    def clearOptimizer(self):
+        """LOne.java:259-263"""
+        self.data = None
+        self.sm_x = None
+        self.x = None
+
+
+def nccl_unique_id() -> bytes:
+    buf = (C.c_uint8 * 128)()
+    _lib.check(_lib.load().sqw_nccl_unique_id(buf))
+    return bytes(buf)
+
+
+def block_evaluate(data, cls, weights, structure: ClassRelationStructure, num_classes: int,
+                   num_threads: int, cx: np.ndarray, sm_x: np.ndarray, pho: float):
+    """(f, g) of LOne.OptObject (LOne.java:936-1049) for every ADMM block at block weights
+    ``cx[t]`` with z = u = 0: the x-update's evaluation kernel on its own, for parity tests.
+    Blocks come back in the library's block order (``java_block_order``)."""
+    lib = _lib.load()
+    data = np.ascontiguousarray(data, dtype=np.float64)
+    n_rows, dim = data.shape
+    st = structure.to_arrays()
+
+    def ip(a):
+        a = np.ascontiguousarray(a, dtype=np.int32)
+        return a if a.size else np.zeros(1, dtype=np.int32)
+
+    arrs = [ip(st[k]) for k in ("node_index", "is_leaf", "layer", "parent_ptr", "parent_idx",
+                                "child_ptr", "child_idx")]
+    cls = np.ascontiguousarray(cls, dtype=np.int32)
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    cx = np.ascontiguousarray(cx, dtype=np.float64)
+    sm_x = np.ascontiguousarray(sm_x, dtype=np.float64)
+    f = np.zeros(num_threads)
+    g = np.zeros((num_threads, num_classes * dim))
+    h = C.c_void_p()
+    _lib.check(lib.sqw_admm_create(C.byref(h)))
+    try:
+        _lib.check(lib.sqw_admm_set_structure(h, st["num_nodes"], st["num_layers"],
+                                              *[a.ctypes.data_as(_lib.i32p) for a in arrs]))
+        _lib.check(lib.sqw_admm_set_params(h, 0.0, pho, num_threads, 1, 1, 0))
+        _lib.check(lib.sqw_admm_set_problem(h, n_rows, dim, num_classes,
+                                            data.ctypes.data_as(_lib.f64p),
+                                            cls.ctypes.data_as(_lib.i32p),
+                                            w.ctypes.data_as(_lib.f64p)))
+        _lib.check(lib.sqw_admm_eval(h, cx.ctypes.data_as(_lib.f64p),
+                                     sm_x.ctypes.data_as(_lib.f64p), pho,
+                                     f.ctypes.data_as(_lib.f64p), g.ctypes.data_as(_lib.f64p)))
+    finally:
+        lib.sqw_admm_destroy(h)
+    return f, g
+
+
+def java_block_order(T: int) -> List[int]:
+    """Order in which the reference sums its per-thread buffers: iteration order of a
+    java.util.HashMap keyed "Thread0".."Thread{T-1}" (LOne.java:399,411,427). The library stores
+    and reports blocks in this order."""
+    from .structure import _java_hashmap_order
+    keys = [f"Thread{t}" for t in range(T)]
+    return [int(k[6:]) for k in _java_hashmap_order(keys)]
+
+
+def lbfgs_rosenbrock(x0: np.ndarray, eps: float = 0.1):
+    """Runs the device L-BFGS / Moré–Thuente solver on the Rosenbrock chain (test hook)."""
+    lib = _lib.load()
+    x = np.array(x0, dtype=np.float64, copy=True)
+    nfev, iters, iflag = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+    _lib.check(lib.sqw_lbfgs_rosenbrock(x.size, x.ctypes.data_as(_lib.f64p), eps,
+                                        C.byref(nfev), C.byref(iters), C.byref(iflag)))
+    return x, int(iflag.value), int(nfev.value)
