@@ -1,0 +1,163 @@
+"""Host-side mirror of the caller of the trainer boundary, ``Classifier.buildClassifier``
+(framework/Classifier.java:291-478, relative to
+/root/reference/src/org/seqcode/projects/sequnwinder/), without Weka:
+
+* RemoveUseless on numeric attributes == drop columns that are constant over the training rows
+  (Classifier.java:305-308);
+* instance-weighted mean / SD with the (W-1) denominator and abs() guard, in-place
+  standardisation (:337-381);
+* null-model initialisation of x and sm_x from unweighted class counts (:383-420);
+* optimizer wiring in the reference's order (:422-449) — here always ``LOneCuda``;
+* de-standardisation into m_Par / sm_Par (:452-477) and ``evaluateProbability`` (:267-287).
+
+This is host glue (NumPy), not a hot path; the training itself runs on the GPU through
+``LOneCuda``. Row sums use NumPy's pairwise summation, so means/SDs agree with the reference's
+sequential loops to rounding (checked against the oracle in tests/).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from .optimizer import LOneCuda
+from .structure import ClassRelationStructure
+
+
+@dataclass
+class Prepared:
+    data: np.ndarray     # standardised, column 0 == 1
+    keep: np.ndarray     # indices of the surviving count columns
+    mean: np.ndarray
+    sd: np.ndarray
+    x0: np.ndarray
+    sm_x0: np.ndarray
+
+
+def prepare(counts: np.ndarray, cls: np.ndarray, weights: np.ndarray,
+            structure: ClassRelationStructure, num_classes: int) -> Prepared:
+    """Classifier.java:300-420 on a dense count matrix."""
+    counts = np.asarray(counts)
+    n = counts.shape[0]
+    keep = np.nonzero(counts.max(axis=0) != counts.min(axis=0))[0]
+    nR = keep.size
+    data = np.empty((n, nR + 1), dtype=np.float64)
+    data[:, 0] = 1.0
+    data[:, 1:] = counts[:, keep]
+    w = np.asarray(weights, dtype=np.float64)
+    tot = float(w.sum())
+    if tot <= 1 and n > 1:
+        raise ValueError("Sum of weights of instances less than 1, please reweight!")
+    mean = np.zeros(nR + 1)
+    sd = np.ones(nR + 1)
+    xs = data[:, 1:]
+    m = (w[:, None] * xs).sum(axis=0) / tot
+    if tot > 1:
+        s = np.sqrt(np.abs((w[:, None] * xs * xs).sum(axis=0) - tot * m * m) / (tot - 1))
+    else:
+        s = np.zeros(nR)
+    mean[1:], sd[1:] = m, s
+    nz = sd != 0
+    data[:, nz] = (data[:, nz] - mean[nz]) / sd[nz]
+
+    dim = nR + 1
+    NN = structure.numNodes
+    sY = np.bincount(np.asarray(cls), minlength=num_classes).astype(np.float64)
+    sm_sY = np.zeros(NN)
+    for leaf in structure.leafs:
+        sm_sY[leaf.nodeIndex] = sY[leaf.nodeIndex]
+    for l in range(1, structure.numLayers):
+        for node in structure.layers[l]:
+            for c in node.children:
+                sm_sY[node.nodeIndex] += sm_sY[c]
+    x0 = np.zeros(num_classes * dim)
+    x0[0::dim] = np.log(sY + 1.0) - np.log(sY[num_classes - 1] + 1.0)
+    sm_x0 = np.zeros(NN * dim)
+    sm_x0[0::dim] = np.log(sm_sY + 1.0) - np.log(sm_sY[num_classes - 1] + 1.0)
+    return Prepared(data, keep, mean, sd, x0, sm_x0)
+
+
+def destandardize(v: np.ndarray, ncols: int, dim: int, mean: np.ndarray, sd: np.ndarray):
+    """Classifier.java:452-477 -> par[dim, ncols] (m_Par / sm_Par layout)."""
+    V = np.asarray(v, dtype=np.float64).reshape(ncols, dim)
+    par = V.T.copy()
+    nz = sd[1:] != 0
+    par[1:][nz] = par[1:][nz] / sd[1:][nz, None]
+    par[0] -= (par[1:][nz] * mean[1:][nz, None]).sum(axis=0)
+    return par
+
+
+def evaluate_probability(par: np.ndarray, raw: np.ndarray) -> np.ndarray:
+    """Classifier.java:267-287 for many rows: raw has column 0 == 1."""
+    v = raw @ par
+    v = v - v.max(axis=1, keepdims=True)
+    e = np.exp(v)
+    return e / e.sum(axis=1, keepdims=True)
+
+
+class Classifier:
+    """Weka-free stand-in for framework/Classifier.java with the options of
+    SeqUnwinderConfig.java:388-413 (-R -PHO -threads -A -S)."""
+
+    def __init__(self, structure: ClassRelationStructure, ridge: float = 10.0, pho: float = 1.7,
+                 num_threads: int = 5, admm_max_its: int = 400, sequnwinder_max_its: int = 15,
+                 debug: bool = False):
+        self.sm_ClassStructure = structure
+        self.m_Ridge, self.m_ADMM_pho = ridge, pho
+        self.m_ADMM_numThreads = num_threads
+        self.m_ADMM_MaxIts, self.m_SeqUnwinder_MaxIts = admm_max_its, sequnwinder_max_its
+        self.m_BGFS_MaxIts = -1
+        self.sm_Debug = debug
+        self.m_Par: Optional[np.ndarray] = None
+        self.sm_Par: Optional[np.ndarray] = None
+        self.prep: Optional[Prepared] = None
+        self.optimizer: Optional[LOneCuda] = None
+        self.comm = None   # (rank, world, nccl_id) for multi-GPU runs
+
+    def buildClassifier(self, counts: np.ndarray, cls: np.ndarray, weights: np.ndarray,
+                        num_classes: int):
+        prep = prepare(counts, cls, weights, self.sm_ClassStructure, num_classes)
+        self.prep = prep
+        x, sm_x = prep.x0.copy(), prep.sm_x0.copy()
+        opt = LOneCuda(x, sm_x, prep.data)                  # Classifier.java:424-425
+        opt.setRidge(self.m_Ridge)                          # :427
+        opt.setADMMmaxItrs(self.m_ADMM_MaxIts)              # :429
+        opt.setBGFSmaxItrs(self.m_BGFS_MaxIts)              # :431
+        opt.setSeqUnwinderMaxIts(self.m_SeqUnwinder_MaxIts)  # :432
+        opt.setClassStructure(self.sm_ClassStructure)       # :433
+        opt.setClsMembership(np.asarray(cls, dtype=np.int32))  # :434
+        opt.setInstanceWeights(np.asarray(weights, dtype=np.float64))  # :435
+        opt.setNumClasses(num_classes)                      # :436
+        opt.setNumPredictors(prep.data.shape[1] - 1)        # :437
+        opt.setPho(self.m_ADMM_pho)                         # :439
+        opt.set_numThreads(self.m_ADMM_numThreads)          # :440
+        opt.initUandZ()                                     # :441
+        opt.setDebugMode(self.sm_Debug)                     # :443
+        if self.comm is not None:
+            opt.setComm(*self.comm)
+        opt.execute()                                       # :444
+        x, sm_x = opt.getX(), opt.getsmX()                  # :447-448
+        dim = prep.data.shape[1]
+        self.m_Par = destandardize(x, num_classes, dim, prep.mean, prep.sd)
+        self.sm_Par = destandardize(sm_x, self.sm_ClassStructure.numNodes, dim, prep.mean, prep.sd)
+        self.optimizer = opt
+        self.x, self.sm_x = x.copy(), sm_x.copy()
+        opt.clearOptimizer()                                # :449
+        return self
+
+    def distributionForInstances(self, counts: np.ndarray) -> np.ndarray:
+        """Classifier.java:244-265 for a batch of raw count rows."""
+        raw = np.empty((counts.shape[0], self.prep.keep.size + 1))
+        raw[:, 0] = 1.0
+        raw[:, 1:] = counts[:, self.prep.keep]
+        return evaluate_probability(self.m_Par, raw)
+
+    def getWeights(self, kmer_names: List[str]) -> Dict[str, np.ndarray]:
+        """Classifier.java:173-193: per node, a numK-long vector of k-mer weights."""
+        out = {}
+        for idx, name in enumerate(self.sm_ClassStructure.node_names()):
+            v = np.zeros(len(kmer_names))
+            v[self.prep.keep] = self.sm_Par[1:, idx]
+            out[name] = v
+        return out

@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -119,8 +120,10 @@ struct sqw_admm {
     Ctrl *h_ring = nullptr;  // pinned [kRing]
     cudaEvent_t ev_x0[kRing], ev_x1[kRing], ev_snap[kRing];
     cudaEvent_t ev_a, ev_b;
-    int kernel_variant = -1;
+    int eval_mode = -1;        // 0 TMA tiles, 1 streaming + W in smem, 2 streaming + W global
+    int force_mode = -1;       // test hook (SQW_ADMM_EVAL_MODE)
     size_t xupdate_smem = 0;
+    TileSmemLayout layout{};
 
     // results
     sqw_admm_stats stats{};
@@ -141,31 +144,37 @@ struct sqw_admm {
 
 namespace sqw {
 
-typedef void (*XKernel)(AdmmDev);
-typedef void (*EKernel)(AdmmDev, double, double *);
+typedef void (*XKernel)(AdmmDev, TileSmemLayout);
+typedef void (*EKernel)(AdmmDev, TileSmemLayout, double, double *);
 
-static XKernel xupdate_kernel(int nct, bool wsmem)
+static XKernel xupdate_kernel(int nct, int mode)
 {
-    switch (nct * 2 + (wsmem ? 1 : 0)) {
-    case 3: return admm_xupdate_kernel<1, true>;
-    case 2: return admm_xupdate_kernel<1, false>;
-    case 5: return admm_xupdate_kernel<2, true>;
-    case 4: return admm_xupdate_kernel<2, false>;
-    case 7: return admm_xupdate_kernel<3, true>;
-    case 6: return admm_xupdate_kernel<3, false>;
+    switch (nct * 3 + mode) {
+    case 3: return admm_xupdate_kernel<1, 0>;
+    case 4: return admm_xupdate_kernel<1, 1>;
+    case 5: return admm_xupdate_kernel<1, 2>;
+    case 6: return admm_xupdate_kernel<2, 0>;
+    case 7: return admm_xupdate_kernel<2, 1>;
+    case 8: return admm_xupdate_kernel<2, 2>;
+    case 9: return admm_xupdate_kernel<3, 0>;
+    case 10: return admm_xupdate_kernel<3, 1>;
+    case 11: return admm_xupdate_kernel<3, 2>;
     }
     return nullptr;
 }
 
-static EKernel eval_kernel(int nct, bool wsmem)
+static EKernel eval_kernel(int nct, int mode)
 {
-    switch (nct * 2 + (wsmem ? 1 : 0)) {
-    case 3: return admm_eval_kernel<1, true>;
-    case 2: return admm_eval_kernel<1, false>;
-    case 5: return admm_eval_kernel<2, true>;
-    case 4: return admm_eval_kernel<2, false>;
-    case 7: return admm_eval_kernel<3, true>;
-    case 6: return admm_eval_kernel<3, false>;
+    switch (nct * 3 + mode) {
+    case 3: return admm_eval_kernel<1, 0>;
+    case 4: return admm_eval_kernel<1, 1>;
+    case 5: return admm_eval_kernel<1, 2>;
+    case 6: return admm_eval_kernel<2, 0>;
+    case 7: return admm_eval_kernel<2, 1>;
+    case 8: return admm_eval_kernel<2, 2>;
+    case 9: return admm_eval_kernel<3, 0>;
+    case 10: return admm_eval_kernel<3, 1>;
+    case 11: return admm_eval_kernel<3, 2>;
     }
     return nullptr;
 }
@@ -200,8 +209,8 @@ static int prepare(sqw_admm *h)
     D.NN = h->NN;
     D.npad = D.C * D.dimp;
     D.upad = D.E * D.dimp;
-    D.wstride = D.dimp + 8;  // dimp is a multiple of 16 doubles: +64 B makes class rows alternate
-                             // between the two halves of the 128-byte bank window
+    D.wstride = D.dimp;  // dimp = 8 (mod 16) doubles: rows alternate between the two 64-byte
+                         // halves of the 128-byte bank window, for X tiles and W alike
     D.world = h->world;
     D.ridge = h->ridge;
     const int nct = D.Cp / 8;
@@ -213,12 +222,33 @@ static int prepare(sqw_admm *h)
     cudaDeviceProp prop;
     SQW_CUDA_CHECK(cudaGetDeviceProperties(&prop, h->device));
     const int n_sm = prop.multiProcessorCount;
+    const size_t budget = (size_t)prop.sharedMemPerBlockOptin - 2048;  // static SolveSmem etc.
     const size_t w_bytes = (size_t)D.Cp * D.wstride * sizeof(double);
-    const bool wsmem = w_bytes <= 160 * 1024;
-    h->xupdate_smem = wsmem ? w_bytes : 0;
-    h->kernel_variant = nct * 2 + (wsmem ? 1 : 0);
-    XKernel xk = xupdate_kernel(nct, wsmem);
-    EKernel ek = eval_kernel(nct, wsmem);
+    TileSmemLayout L = tile_smem_layout(D.Cp, D.dimp, budget, kSolveScratchBytes);
+    const int ngroups = (D.dimp + 15) / 16;
+    const int nbg = (nct <= 2) ? 6 : 4;
+    int mode;
+    if (L.NS >= 2 && ngroups <= kWarps * nbg)
+        mode = 0;
+    else if (w_bytes <= 160 * 1024)
+        mode = 1;
+    else
+        mode = 2;
+    if (const char *env = getenv("SQW_ADMM_EVAL_MODE")) {
+        const int m = atoi(env);
+        if (m >= mode && m <= 2)
+            mode = m;  // only towards the more general paths
+    }
+    h->eval_mode = mode;
+    if (mode == 0)
+        h->xupdate_smem = L.total;
+    else if (mode == 1)
+        h->xupdate_smem = std::max(w_bytes, kSolveScratchBytes);
+    else
+        h->xupdate_smem = kSolveScratchBytes;
+    h->layout = L;
+    XKernel xk = xupdate_kernel(nct, mode);
+    EKernel ek = eval_kernel(nct, mode);
     SQW_CUDA_CHECK(cudaFuncSetAttribute(xk, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)h->xupdate_smem));
     SQW_CUDA_CHECK(cudaFuncSetAttribute(ek, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -278,6 +308,8 @@ static int prepare(sqw_admm *h)
     TRY(h->dalloc(&D.spart, TL * D.G * kNumDots));
     TRY(h->dalloc(&D.bar, TL * 32));
     TRY(h->dalloc(&D.nfev, TL));
+    if (getenv("SQW_ADMM_PROFILE"))
+        TRY(h->dalloc(&D.prof, TL * D.G * 8));
     TRY(h->dalloc(&D.sum1, (size_t)D.npad + D.upad));
     TRY(h->dalloc(&D.sum2, (size_t)D.E));
     TRY(h->dalloc(&D.edge_stats, (size_t)D.E * 4));
@@ -307,8 +339,8 @@ static int prepare(sqw_admm *h)
 static int launch_xupdate(sqw_admm *h)
 {
     AdmmDev &D = h->dev;
-    XKernel xk = xupdate_kernel(D.Cp / 8, h->xupdate_smem > 0);
-    void *args[] = {&D};
+    XKernel xk = xupdate_kernel(D.Cp / 8, h->eval_mode);
+    void *args[] = {&D, &h->layout};
     SQW_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)xk, dim3(D.T_local * D.G), dim3(kThreads),
                                                args, h->xupdate_smem, h->stream));
     return SQW_OK;
@@ -569,7 +601,10 @@ static int plan_blocks(sqw_admm *h, int64_t n_rows, int32_t dim, int32_t num_cla
     D.T_local = (int)h->block_ids.size();
     D.nb = (int)(n_rows / h->T);
     D.dim = dim;
-    D.dimp = (dim + 15) / 16 * 16;
+    // padded row length: a multiple of 8 doubles with dimp/8 odd (see admm_eval_tma.cuh)
+    D.dimp = (dim + 7) / 8 * 8;
+    if (((D.dimp / 8) & 1) == 0)
+        D.dimp += 8;
     return SQW_OK;
 }
 
@@ -805,6 +840,19 @@ int sqw_admm_execute(sqw_admm *h, double *x_inout, double *smx_inout)
     if ((rc = download_padded(h, D.xbar, D.C, D.dim, D.dimp, x_inout)) != SQW_OK) return rc;
     if ((rc = download_padded(h, D.smx, D.NN, D.dim, D.dimp, smx_inout)) != SQW_OK) return rc;
 
+    if (D.prof) {
+        std::vector<long long> pr((size_t)D.T_local * D.G * 8);
+        SQW_CUDA_CHECK(cudaMemcpy(pr.data(), D.prof, pr.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        const char *names[7] = {"eval", "barrier1", "reduce", "barrier2", "decide", "update", "barrier3"};
+        for (int c : {0, D.G / 2, D.G - 1}) {
+            const long long *q = &pr[(size_t)c * 8];
+            fprintf(stderr, "[sqw profile] block 0 cta %d: evals %lld;", c, q[7]);
+            for (int i = 0; i < 7; ++i)
+                fprintf(stderr, " %s %.0f cyc", names[i], q[7] ? (double)q[i] / q[7] : 0.0);
+            fprintf(stderr, "\n");
+        }
+        SQW_CUDA_CHECK(cudaMemset(D.prof, 0, pr.size() * sizeof(long long)));
+    }
     // logs
     const int rows = last.log_rows;
     h->log_outer.resize(rows); h->log_itr.resize(rows);
@@ -897,8 +945,8 @@ int sqw_admm_eval(sqw_admm *h, const double *cx, const double *smx, double pho, 
     double *d_f = nullptr;
     SQW_CUDA_CHECK(cudaMalloc((void **)&d_f, sizeof(double) * D.T_local));
     SQW_CUDA_CHECK(cudaMemsetAsync(d_f, 0, sizeof(double) * D.T_local, st));
-    EKernel ek = eval_kernel(D.Cp / 8, h->xupdate_smem > 0);
-    void *args[] = {&D, &pho, &d_f};
+    EKernel ek = eval_kernel(D.Cp / 8, h->eval_mode);
+    void *args[] = {&D, &h->layout, &pho, &d_f};
     cudaError_t e = cudaLaunchCooperativeKernel((void *)ek, dim3(D.T_local * D.G), dim3(kThreads),
                                                 args, h->xupdate_smem, st);
     if (e == cudaSuccess)
@@ -947,6 +995,7 @@ int sqw_lbfgs_rosenbrock(int32_t n, double *x_inout, double eps, int32_t *nfev_o
     ws.spart = buf + (5 + 2 * kLbfgsM) * nv;
     ws.G = G;
     ws.cta = 0;
+    ws.prof = nullptr;
     SQW_CUDA_CHECK(cudaMemcpy(ws.x, x_inout, nv * sizeof(double), cudaMemcpyHostToDevice));
     void *args[] = {&ws, &bar, &eps, &out};
     cudaError_t e = cudaLaunchCooperativeKernel((void *)lbfgs_rosenbrock_kernel, dim3(G),

@@ -164,7 +164,7 @@ __device__ double eval_data_term(const AdmmDev &P, int blk, int cta, const doubl
     const double fsum = block_sum(facc, red);  // also orders the R stores before pass 2
 
     // ---------------- pass 2: G = R^T X over the CTA's rows ----------------
-    const int ngroups = dimp >> 4;
+    const int ngroups = (dimp + 15) >> 4;  // the last group is half wide when dimp = 8 (mod 16)
     const int nrq = (r1 - r0 + 3) >> 2;
     double *gp = P.gpart + ((size_t)blk * P.G + cta) * P.npad;
     for (int gb = 0; gb < ngroups; gb += kWarps * NBG) {
@@ -192,7 +192,9 @@ __device__ double eval_data_term(const AdmmDev &P, int blk, int cta, const doubl
             for (int i = 0; i < NBG; ++i) {
                 const int grp = gb + warp + kWarps * i;
                 if (grp < ngroups) {
-                    const double2 xb = __ldg(xr + 8 * grp);
+                    double2 xb = make_double2(0.0, 0.0);
+                    if (16 * grp + 2 * gid < dimp)
+                        xb = __ldg(xr + 8 * grp);
 #pragma unroll
                     for (int ct = 0; ct < NCT; ++ct) {
                         dmma884(acc[i][0][ct], a[ct], xb.x);
@@ -205,7 +207,7 @@ __device__ double eval_data_term(const AdmmDev &P, int blk, int cta, const doubl
 #pragma unroll
         for (int i = 0; i < NBG; ++i) {
             const int grp = gb + warp + kWarps * i;
-            if (grp < ngroups) {
+            if (grp < ngroups && 16 * grp + 4 * q < dimp) {
 #pragma unroll
                 for (int ct = 0; ct < NCT; ++ct) {
                     const int c = ct * 8 + gid;

@@ -21,6 +21,7 @@
 // of iteration k (:614-615) still precedes that test, as in the reference.
 #pragma once
 
+#include "admm_eval_tma.cuh"
 #include "admm_solver.cuh"
 
 namespace sqw {
@@ -31,7 +32,12 @@ __device__ __forceinline__ int ld_volatile_int(const int *p)
 }
 
 // ------------------------------------------------------------------ x-update
-template <int NCT, bool W_SMEM>
+// Evaluation modes of the x-update kernel:
+//   MODE 0  fused single pass over TMA-staged 8-row tiles (admm_eval_tma.cuh): rows up to ~768
+//           columns, i.e. k = 4..5 feature sets;
+//   MODE 1  two streaming passes from global memory, W in shared memory (admm_eval.cuh);
+//   MODE 2  the same with W read from global memory (row lengths beyond shared memory).
+template <int NCT, int MODE>
 struct BlockProblem {
     const AdmmDev &P;
     int blk, cta;
@@ -39,21 +45,31 @@ struct BlockProblem {
     double *red;
     double pho;
     const double *ut;
+    TileEval<NCT> *tile;
 
     __device__ double eval_partial(const double *x)
     {
-        return eval_data_term<NCT, W_SMEM>(P, blk, cta, x, smW, red);
+        if (MODE == 0)
+            return tile->eval(x);
+        return eval_data_term<NCT, MODE == 1>(P, blk, cta, x, smW, red);
     }
 
-    // gradient of coordinate k: data term reduced over the group's partials, plus the augmented
-    // Lagrangian term rho*(x - sm_x[par] - z + u_t) for w >= 1 (LOne.java:982-998); faug
-    // accumulates rho/2 * (...)^2 (LOne.java:1031-1047).
+    // gradient of coordinate k: data term reduced over the group's partials (fixed order), plus
+    // the augmented Lagrangian term rho*(x - sm_x[par] - z + u_t) for w >= 1 (LOne.java:982-998);
+    // faug accumulates rho/2 * (...)^2 (LOne.java:1031-1047).
     __device__ double grad_coord(int k, const double *x, double &faug)
     {
         const double *gp = P.gpart + (size_t)blk * P.G * P.npad + k;
         double s = 0.0;
-        for (int c = 0; c < P.G; ++c)
-            s += __ldcg(gp + (size_t)c * P.npad);
+        for (int c0 = 0; c0 < P.G; c0 += 8) {
+            double v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                v[j] = (c0 + j < P.G) ? __ldcg(gp + (size_t)(c0 + j) * P.npad) : 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                s += v[j];
+        }
         const int leaf = k / P.dimp, w = k - leaf * P.dimp;
         if (w >= 1 && w < P.dim) {
             const double xk = __ldcg(x + k);
@@ -72,10 +88,10 @@ struct BlockProblem {
     }
 };
 
-template <int NCT, bool W_SMEM>
-__global__ void __launch_bounds__(kThreads, 1) admm_xupdate_kernel(AdmmDev P)
+template <int NCT, int MODE>
+__global__ void __launch_bounds__(kThreads, 1) admm_xupdate_kernel(AdmmDev P, TileSmemLayout L)
 {
-    extern __shared__ __align__(16) double smW[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ SolveSmem sm;
     if (ld_volatile_int(&P.ctrl->done) || ld_volatile_int(&P.ctrl->fatal))
         return;
@@ -83,6 +99,10 @@ __global__ void __launch_bounds__(kThreads, 1) admm_xupdate_kernel(AdmmDev P)
     const double pho = P.ctrl->pho, fold = P.ctrl->fold;
     double *xt = P.xt + (size_t)blk * P.Cp * P.dimp;
     double *ut = P.ut + (size_t)blk * P.upad;
+    sm.scratch = reinterpret_cast<double *>(smem_raw);
+    TileEval<NCT> tile{P, blk, cta};
+    if (MODE == 0)
+        tile.init(smem_raw, L, sm.red);
 
     // u-update (LOne.java:833-861): x-hat_t = a x_t + (1-a) z_old - a sm_x[par];
     // u_t += x-hat_t - z; u_t /= rho_fold.  Slice of the edge coordinates per CTA.
@@ -103,7 +123,7 @@ __global__ void __launch_bounds__(kThreads, 1) admm_xupdate_kernel(AdmmDev P)
     }
 
     GroupBarrier gb{P.bar + blk * 32, 0u, P.G};
-    BlockProblem<NCT, W_SMEM> prob{P, blk, cta, smW, sm.red, pho, ut};
+    BlockProblem<NCT, MODE> prob{P, blk, cta, reinterpret_cast<double *>(smem_raw), sm.red, pho, ut, &tile};
     SolveWs ws;
     ws.n = P.npad;
     ws.x = xt;
@@ -116,8 +136,11 @@ __global__ void __launch_bounds__(kThreads, 1) admm_xupdate_kernel(AdmmDev P)
     ws.spart = P.spart + (size_t)blk * P.G * kNumDots;
     ws.G = P.G;
     ws.cta = cta;
+    ws.prof = P.prof ? P.prof + (size_t)blockIdx.x * 8 : nullptr;
     int status = 0;
     const int evals = lbfgs_group_solve(prob, ws, gb, sm, 0.1, 10e-16, status);  // LOne.java:874-875
+    if (MODE == 0)
+        tile.drain();
     if (cta == 0 && threadIdx.x == 0) {
         P.nfev[blk] = evals;
         if (status == 1)
@@ -401,16 +424,28 @@ admm_block_rows_kernel(const double *src, const int *ysrc, const double *wsrc, i
 
 // ------------------------------------------------------------------ test kernels
 // One evaluation per local block at the current x_t with the device's z / u_t / sm_x state.
-template <int NCT, bool W_SMEM>
-__global__ void __launch_bounds__(kThreads, 1) admm_eval_kernel(AdmmDev P, double pho, double *f_out)
+template <int NCT, int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+admm_eval_kernel(AdmmDev P, TileSmemLayout L, double pho, double *f_out)
 {
-    extern __shared__ __align__(16) double smW[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ SolveSmem sm;
     const int blk = blockIdx.x / P.G, cta = blockIdx.x - blk * P.G;
     double *xt = P.xt + (size_t)blk * P.Cp * P.dimp;
     GroupBarrier gb{P.bar + blk * 32, 0u, P.G};
-    BlockProblem<NCT, W_SMEM> prob{P, blk, cta, smW, sm.red, pho, P.ut + (size_t)blk * P.upad};
-    const double fpart = prob.eval_partial(xt);
+    TileEval<NCT> tile{P, blk, cta};
+    if (MODE == 0)
+        tile.init(smem_raw, L, sm.red);
+    BlockProblem<NCT, MODE> prob{P, blk, cta, reinterpret_cast<double *>(smem_raw), sm.red, pho,
+                                 P.ut + (size_t)blk * P.upad, &tile};
+    double fpart = prob.eval_partial(xt);
+    if (MODE == 0) {
+        // second evaluation exercises the ring wrap-around / resident path; results must agree
+        const double f2 = prob.eval_partial(xt);
+        if (f2 != fpart)
+            fpart = nan("");
+        tile.drain();
+    }
     gb.sync();
     const int n = P.npad;
     const int sl = ((n + P.G - 1) / P.G + 15) & ~15;
@@ -443,6 +478,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 lbfgs_rosenbrock_kernel(SolveWs ws, unsigned *bar, double eps, int *out)
 {
     __shared__ SolveSmem sm;
+    __shared__ double scratch[kNumDots * (kThreads / 2)];
+    sm.scratch = scratch;
     RosenProblem prob{ws.n};
     ws.cta = blockIdx.x;
     GroupBarrier gb{bar, 0u, ws.G};

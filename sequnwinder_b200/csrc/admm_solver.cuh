@@ -308,14 +308,17 @@ static_assert(D_DY + kLbfgsM == kNumDots, "dot table");
 
 enum Action : int { ACT_LINESEARCH = 0, ACT_NEWDIR = 1, ACT_FINISH = 2, ACT_FAIL = 3 };
 
-// Scalar L-BFGS state (identical in every CTA of the group).
+// Scalar L-BFGS state (identical in every CTA of the group). The Gram matrices are kept in AGE
+// order (index 0 = newest pair) so that every loop below has compile-time bounds and the whole
+// state lives in registers of the one thread that runs the scalar step; slot <-> age is
+// slot(a) = (point - 1 - a) mod m.
 struct LbState {
     int iter, point, hist, nfun, evals;
     double stp, f;
     McState mc;
-    double SY[kLbfgsM][kLbfgsM];  // s_i . y_j
-    double YY[kLbfgsM][kLbfgsM];  // y_i . y_j
-    double sg[kLbfgsM], yg[kLbfgsM], rho[kLbfgsM];
+    double SY[kLbfgsM][kLbfgsM];  // s_(age i) . y_(age j)
+    double YY[kLbfgsM][kLbfgsM];  // y_(age i) . y_(age j)
+    double rho[kLbfgsM];
 };
 
 // What thread 0 tells the rest of the CTA after the scalar step.
@@ -325,7 +328,7 @@ struct Decision {
     int hist;            // number of valid pairs after the update
     double stp_accept;   // step that scales d into s_new
     double stp;          // trial step for the next evaluation
-    double cg;           // d_new = cg * g + sum cs[i] * s_i + sum cy[i] * y_i
+    double cg;           // d_new = cg * g + sum cs[i] * s_i + sum cy[i] * y_i   (i = slot)
     double cs[kLbfgsM], cy[kLbfgsM];
     unsigned valid_mask; // slots taking part in d_new / in the next reduce (bit i)
 };
@@ -339,12 +342,13 @@ __device__ __forceinline__ unsigned hist_mask(int point, int hist)
     return m;
 }
 
-// The scalar step after an evaluation whose reduced scalars are dots[]. Mirrors the tail of
-// LBFGS.lbfgs (LBFGS.java:531-590) followed by the head of its next loop trip (:407-527).
-__device__ inline void lbfgs_scalar_step(LbState &st, const double *dots, double eps, double xtol,
-                                         Decision &dec, int &fatal, bool first)
+// The scalar step after an evaluation whose reduced scalars are dots[] (shared memory). Mirrors
+// the tail of LBFGS.lbfgs (LBFGS.java:531-590) followed by the head of its next loop trip
+// (:407-527), with the two-loop recursion evaluated on the Gram matrices.
+__device__ __forceinline__ void lbfgs_scalar_step(LbState &st, const double *dots, double eps,
+                                                  double xtol, Decision &dec, int &fatal, bool first)
 {
-    const int m = kLbfgsM;
+    constexpr int m = kLbfgsM;
     st.evals++;
     st.f = dots[D_F];
     if (first) {
@@ -379,26 +383,40 @@ __device__ inline void lbfgs_scalar_step(LbState &st, const double *dots, double
         return;
     }
 
-    // line search finished: s = stp*d, y = g - g_old stored at slot p (LBFGS.java:551-563)
+    // line search finished: s = stp*d, y = g - g_old stored at slot p (LBFGS.java:551-563).
+    // Old pairs age by one (the oldest drops out when the history is full); the new pair is age 0.
     const int p = st.point;
     const double stp = st.stp;
-    const unsigned old = hist_mask(st.point, st.hist) & ~(1u << p);
     st.nfun += st.mc.nfev;
-    for (int i = 0; i < m; ++i) {
-        if (!((old >> i) & 1u))
-            continue;
-        st.SY[p][i] = stp * dots[D_DY + i];
-        st.SY[i][p] = dots[D_YNS + i];
-        st.YY[p][i] = st.YY[i][p] = dots[D_YNY + i];
-        st.sg[i] = dots[D_GS + i];
-        st.yg[i] = dots[D_GY + i];
+    const int nold = min(st.hist, m - 1);  // old pairs that survive
+#pragma unroll
+    for (int i = m - 1; i >= 1; --i) {
+#pragma unroll
+        for (int j = m - 1; j >= 1; --j) {
+            st.SY[i][j] = st.SY[i - 1][j - 1];
+            st.YY[i][j] = st.YY[i - 1][j - 1];
+        }
+        st.rho[i] = st.rho[i - 1];
     }
-    st.SY[p][p] = stp * dots[D_DYN];
-    st.YY[p][p] = dots[D_YNYN];
-    st.sg[p] = stp * dots[D_GD];
-    st.yg[p] = dots[D_GYN];
-    st.hist = min(st.hist + 1, m);
-    st.point = (p + 1) % m;
+    double sg[m], yg[m];
+#pragma unroll
+    for (int a = 0; a < m - 1; ++a) {
+        // old pair of (old) age a sits in slot (p - 1 - a) mod m and becomes age a + 1
+        int slot = p - 1 - a;
+        slot += (slot < 0) ? m : 0;
+        const bool ok = a < nold;
+        st.SY[0][a + 1] = ok ? stp * dots[D_DY + slot] : 0.0;   // s_new . y_old
+        st.SY[a + 1][0] = ok ? dots[D_YNS + slot] : 0.0;        // s_old . y_new
+        st.YY[0][a + 1] = st.YY[a + 1][0] = ok ? dots[D_YNY + slot] : 0.0;
+        sg[a + 1] = ok ? dots[D_GS + slot] : 0.0;
+        yg[a + 1] = ok ? dots[D_GY + slot] : 0.0;
+    }
+    st.SY[0][0] = stp * dots[D_DYN];
+    st.YY[0][0] = dots[D_YNYN];
+    sg[0] = stp * dots[D_GD];
+    yg[0] = dots[D_GYN];
+    st.hist = nold + 1;
+    st.point = (p + 1 == m) ? 0 : p + 1;
     dec.slot = p;
     dec.hist = st.hist;
     dec.stp_accept = stp;
@@ -413,7 +431,7 @@ __device__ inline void lbfgs_scalar_step(LbState &st, const double *dots, double
 
     // next trip of the loop (LBFGS.java:407-506): H0 = ys/yy, two-loop recursion on scalars
     st.iter++;
-    const double ys = st.SY[p][p], yy = st.YY[p][p];
+    const double ys = st.SY[0][0], yy = st.YY[0][0];
     double diag = ys / yy;
     if (isnan(diag) || isinf(diag)) {  // safeDiv (LBFGS.java:804-814)
         if (ys == 0.0 && yy == 0.0)
@@ -421,43 +439,44 @@ __device__ inline void lbfgs_scalar_step(LbState &st, const double *dots, double
         else
             fatal = 1;
     }
-    st.rho[p] = 1.0 / ys;
-    const unsigned valid = hist_mask(st.point, st.hist);
-    double alpha[kLbfgsM], beta[kLbfgsM];
-    for (int i = 0; i < m; ++i)
-        alpha[i] = beta[i] = 0.0;
-    // first loop: newest -> oldest; q = -g - sum_{processed} alpha_l y_l
-    for (int j = 0; j < st.hist; ++j) {
-        const int cp = (st.point - 1 - j + 2 * m) % m;
-        double sq = -st.sg[cp];
-        for (int jj = 0; jj < j; ++jj) {
-            const int l = (st.point - 1 - jj + 2 * m) % m;
-            sq -= alpha[l] * st.SY[cp][l];
-        }
-        alpha[cp] = st.rho[cp] * sq;
+    st.rho[0] = 1.0 / ys;
+    const int hist = st.hist;
+    double alpha[m], beta[m];
+    // first loop, newest -> oldest: q = -g - sum_{b<a} alpha_b y_b ; alpha_a = rho_a * (s_a . q)
+#pragma unroll
+    for (int a = 0; a < m; ++a) {
+        double sq = -sg[a];
+#pragma unroll
+        for (int b = 0; b < a; ++b)
+            sq -= alpha[b] * st.SY[a][b];
+        alpha[a] = (a < hist) ? st.rho[a] * sq : 0.0;
     }
-    // second loop: oldest -> newest; r = diag*q + sum_{processed} beta_l s_l
-    for (int j = st.hist - 1; j >= 0; --j) {
-        const int cp = (st.point - 1 - j + 2 * m) % m;
-        double yq = -st.yg[cp];
-        for (int jj = 0; jj < st.hist; ++jj) {
-            const int l = (st.point - 1 - jj + 2 * m) % m;
-            yq -= alpha[l] * st.YY[cp][l];
-        }
+    // second loop, oldest -> newest: r = diag*q + sum_{b>a} beta_b s_b ; beta_a = alpha_a - rho_a (y_a . r)
+#pragma unroll
+    for (int a = m - 1; a >= 0; --a) {
+        double yq = -yg[a];
+#pragma unroll
+        for (int b = 0; b < m; ++b)
+            yq -= alpha[b] * st.YY[a][b];
         double yr = diag * yq;
-        for (int jj = st.hist - 1; jj > j; --jj) {
-            const int l = (st.point - 1 - jj + 2 * m) % m;
-            yr += beta[l] * st.SY[l][cp];
-        }
-        beta[cp] = alpha[cp] - st.rho[cp] * yr;
+#pragma unroll
+        for (int b = m - 1; b > a; --b)
+            yr += beta[b] * st.SY[b][a];
+        beta[a] = (a < hist) ? alpha[a] - st.rho[a] * yr : 0.0;
     }
     dec.cg = -diag;
     double dginit = -diag * dots[D_GG];
-    for (int i = 0; i < m; ++i) {
-        dec.cs[i] = beta[i];
-        dec.cy[i] = -diag * alpha[i];
-        if ((valid >> i) & 1u)
-            dginit += dec.cs[i] * st.sg[i] + dec.cy[i] * st.yg[i];
+    unsigned valid = 0;
+#pragma unroll
+    for (int a = 0; a < m; ++a) {
+        int slot = st.point - 1 - a;
+        slot += (slot < 0) ? m : 0;
+        if (a < hist) {
+            dec.cs[slot] = beta[a];
+            dec.cy[slot] = -diag * alpha[a];
+            dginit += beta[a] * sg[a] + (-diag * alpha[a]) * yg[a];
+            valid |= 1u << slot;
+        }
     }
     dec.valid_mask = valid;
     if (isnan(dginit) || isinf(dginit))
@@ -483,14 +502,18 @@ struct SolveWs {
     double *g, *gold, *d, *wa, *S, *Y;
     double *spart; // [G][kNumDots]
     int G, cta;
+    long long *prof; // optional [8] per CTA: cycles in E, barrier1, R, barrier2, S, update, barrier3, evals
 };
 
 struct SolveSmem {
     double dots[kNumDots];
     double red[kWarps];
     Decision dec;
+    LbState st;       // scalar solver state: shared memory keeps it out of every thread's registers
     int fatal;
+    double *scratch;  // >= kNumDots * (kThreads / 2) doubles of shared memory, free during reduce
 };
+constexpr size_t kSolveScratchBytes = (size_t)kNumDots * (kThreads / 2) * sizeof(double);
 
 // Problem concept:
 //   double eval_partial(const double *x)        phase E, all threads; returns the CTA's partial f
@@ -506,10 +529,10 @@ __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier 
     // coordinate slice of this CTA: whole 128-byte lines, so no line is shared between CTAs
     const int sl = ((n + G - 1) / G + 15) & ~15;
     const int k0 = min(n, cta * sl), k1 = min(n, k0 + sl);
-    LbState st;  // meaningful in thread 0 only
-    st.evals = 0;
-    st.point = 0;
-    st.hist = 0;
+    LbState &st = sm.st;
+    for (int i = threadIdx.x; i < (int)(sizeof(LbState) / sizeof(int)); i += kThreads)
+        reinterpret_cast<int *>(&st)[i] = 0;
+    __syncthreads();
     unsigned valid = 0;   // history slots to reduce against (excludes the slot being replaced)
     int point = 0;        // slot y_new is written to
     bool first = true;
@@ -517,74 +540,107 @@ __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier 
 
     for (;;) {
         // ---- phase E: data-term partials of this CTA at the trial point
+        long long tk0 = 0, tk1 = 0;
+        if (ws.prof && threadIdx.x == 0)
+            tk0 = clock64();
+#define SQW_PROF(slot)                                   \
+    if (ws.prof && threadIdx.x == 0) {                   \
+        tk1 = clock64();                                 \
+        ws.prof[slot] += tk1 - tk0;                      \
+        tk0 = tk1;                                       \
+    }
         const double fpart = prob.eval_partial(ws.x);
+        SQW_PROF(0)
         gb.sync();
+        SQW_PROF(1)
 
-        // ---- phase R: reduced gradient of my slice, y_new, and all scalar partials
-        double faug = 0.0;
+        // ---- phase R: one pass over my coordinate slice produces the reduced gradient, y_new
+        // and every scalar partial (each thread owns 1-2 coordinates; all loads of a coordinate
+        // are issued together, then the 32 partials are reduced through shared memory)
+        double pd[kNumDots];
+#pragma unroll
+        for (int i = 0; i < kNumDots; ++i)
+            pd[i] = 0.0;
         double *ynew = ws.Y + (size_t)point * n;
         for (int k = k0 + threadIdx.x; k < k1; k += kThreads) {
+            double faug = 0.0;
             const double gk = prob.grad_coord(k, ws.x, faug);
+            const double xk = __ldcg(ws.x + k);
             ws.g[k] = gk;
-            if (!first)
-                ynew[k] = gk - ws.gold[k];
-        }
-        const double faug_sum = block_sum(faug, sm.red);  // also orders g / y_new stores
-        for (int id = warp; id < kNumDots; id += kWarps) {
-            const double *a = nullptr, *b = nullptr;
-            bool need = true;
-            if (id == D_F) {
-                need = false;
-            } else if (id == D_GG) {
-                a = ws.g, b = ws.g;
-            } else if (id == D_XX) {
-                a = ws.x, b = ws.x;
-            } else if (first) {
-                need = false;
-            } else if (id == D_GD) {
-                a = ws.g, b = ws.d;
-            } else if (id == D_GYN) {
-                a = ws.g, b = ynew;
-            } else if (id == D_YNYN) {
-                a = ynew, b = ynew;
-            } else if (id == D_DYN) {
-                a = ws.d, b = ynew;
-            } else {
-                const int i = (id - D_GS) % kLbfgsM, kind = (id - D_GS) / kLbfgsM;
-                need = (valid >> i) & 1u;
-                const double *si = ws.S + (size_t)i * n, *yi = ws.Y + (size_t)i * n;
-                a = (kind <= 1) ? ws.g : (kind <= 3 ? ynew : ws.d);
-                b = (kind == 0 || kind == 2) ? si : yi;
+            pd[D_F] += faug;
+            pd[D_GG] += gk * gk;
+            pd[D_XX] += xk * xk;
+            if (!first) {
+                const double dk = ws.d[k];
+                const double yn = gk - ws.gold[k];
+                ynew[k] = yn;
+                pd[D_GD] += gk * dk;
+                pd[D_GYN] += gk * yn;
+                pd[D_YNYN] += yn * yn;
+                pd[D_DYN] += dk * yn;
+#pragma unroll
+                for (int i = 0; i < kLbfgsM; ++i) {
+                    if ((valid >> i) & 1u) {
+                        const double si = ws.S[(size_t)i * n + k], yi = ws.Y[(size_t)i * n + k];
+                        pd[D_GS + i] += gk * si;
+                        pd[D_GY + i] += gk * yi;
+                        pd[D_YNS + i] += yn * si;
+                        pd[D_YNY + i] += yn * yi;
+                        pd[D_DY + i] += dk * yi;
+                    }
+                }
             }
-            double acc = 0.0;
-            if (need)
-                for (int k = k0 + lane; k < k1; k += 32)
-                    acc += a[k] * b[k];
-            acc = warp_sum(acc);
-            if (lane == 0)
-                __stcg(ws.spart + (size_t)cta * kNumDots + id,
-                       id == D_F ? fpart + faug_sum : acc);
         }
+        if (threadIdx.x == 0)
+            pd[D_F] += fpart;
+        {
+            double *scr = sm.scratch;
+            __syncthreads();  // the evaluator is done with the shared region the scratch aliases
+#pragma unroll
+            for (int i = 0; i < kNumDots; ++i) {
+                const double v = pd[i] + __shfl_xor_sync(0xffffffffu, pd[i], 1);
+                if ((lane & 1) == 0)
+                    scr[i * (kThreads / 2) + (threadIdx.x >> 1)] = v;
+            }
+            __syncthreads();
+            for (int id = warp; id < kNumDots; id += kWarps) {
+                double acc = 0.0;
+#pragma unroll
+                for (int j = 0; j < (kThreads / 2) / 32; ++j)
+                    acc += scr[id * (kThreads / 2) + j * 32 + lane];
+                acc = warp_sum(acc);
+                if (lane == 0)
+                    __stcg(ws.spart + (size_t)cta * kNumDots + id, acc);
+            }
+        }
+        SQW_PROF(2)
         gb.sync();
+        SQW_PROF(3)
 
         // ---- phase S: every CTA reduces the G partials identically and takes the same decision
         if (warp == 0) {
             double s = 0.0;
-            for (int c = 0; c < G; ++c)
-                s += __ldcg(ws.spart + (size_t)c * kNumDots + lane);
+            for (int c0 = 0; c0 < G; c0 += 32) {
+                double v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    v[j] = (c0 + j < G) ? __ldcg(ws.spart + (size_t)(c0 + j) * kNumDots + lane) : 0.0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    s += v[j];
+            }
             sm.dots[lane] = s;
+            const int bad = __any_sync(0xffffffffu, isnan(s) || isinf(s));
+            __syncwarp();
+            if (lane == 0) {
+                int fatal = bad;
+                if (!fatal)
+                    lbfgs_scalar_step(st, sm.dots, eps, xtol, sm.dec, fatal, first);
+                sm.fatal = fatal;
+            }
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            int fatal = 0;
-            for (int i = 0; i < kNumDots; ++i)
-                if (isnan(sm.dots[i]) || isinf(sm.dots[i]))
-                    fatal = 1;
-            if (!fatal)
-                lbfgs_scalar_step(st, sm.dots, eps, xtol, sm.dec, fatal, first);
-            sm.fatal = fatal;
-        }
-        __syncthreads();
+        SQW_PROF(4)
         const Decision &dec = sm.dec;
         if (sm.fatal) {
             status = 2;
@@ -617,8 +673,13 @@ __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier 
             valid = dec.valid_mask & ~(1u << point);
         }
         first = false;
+        SQW_PROF(5)
         gb.sync();
+        SQW_PROF(6)
+        if (ws.prof && threadIdx.x == 0)
+            ws.prof[7] += 1;
     }
+#undef SQW_PROF
     int evals = 0;
     if (threadIdx.x == 0)
         sm.dec.hist = st.evals;

@@ -105,6 +105,7 @@ struct AdmmDev {
     double *spart; // [T_local][G][kNumDots] per-CTA partial scalars
     unsigned *bar; // [T_local][32] group barrier counters (one per 128-byte line)
     int *nfev;     // [T_local] evaluations done by the last x-update
+    long long *prof; // optional [T_local*G][8] phase cycle counters (SQW_ADMM_PROFILE=1)
 
     // ---- consensus exchange buffers ----
     double *sum1;  // [npad + upad]  sum over blocks of x_t | u_t   (allreduced when world > 1)
