@@ -149,32 +149,32 @@ typedef void (*EKernel)(AdmmDev, TileSmemLayout, double, double *);
 
 static XKernel xupdate_kernel(int nct, int mode)
 {
-    switch (nct * 3 + mode) {
-    case 3: return admm_xupdate_kernel<1, 0>;
-    case 4: return admm_xupdate_kernel<1, 1>;
-    case 5: return admm_xupdate_kernel<1, 2>;
-    case 6: return admm_xupdate_kernel<2, 0>;
-    case 7: return admm_xupdate_kernel<2, 1>;
-    case 8: return admm_xupdate_kernel<2, 2>;
-    case 9: return admm_xupdate_kernel<3, 0>;
-    case 10: return admm_xupdate_kernel<3, 1>;
-    case 11: return admm_xupdate_kernel<3, 2>;
+    switch (nct * 8 + mode) {
+    case 8 + 4: return admm_xupdate_kernel<1, 4>;
+    case 8 + 1: return admm_xupdate_kernel<1, 1>;
+    case 8 + 2: return admm_xupdate_kernel<1, 2>;
+    case 16 + 4: return admm_xupdate_kernel<2, 4>;
+    case 16 + 1: return admm_xupdate_kernel<2, 1>;
+    case 16 + 2: return admm_xupdate_kernel<2, 2>;
+    case 24 + 4: return admm_xupdate_kernel<3, 4>;
+    case 24 + 1: return admm_xupdate_kernel<3, 1>;
+    case 24 + 2: return admm_xupdate_kernel<3, 2>;
     }
     return nullptr;
 }
 
 static EKernel eval_kernel(int nct, int mode)
 {
-    switch (nct * 3 + mode) {
-    case 3: return admm_eval_kernel<1, 0>;
-    case 4: return admm_eval_kernel<1, 1>;
-    case 5: return admm_eval_kernel<1, 2>;
-    case 6: return admm_eval_kernel<2, 0>;
-    case 7: return admm_eval_kernel<2, 1>;
-    case 8: return admm_eval_kernel<2, 2>;
-    case 9: return admm_eval_kernel<3, 0>;
-    case 10: return admm_eval_kernel<3, 1>;
-    case 11: return admm_eval_kernel<3, 2>;
+    switch (nct * 8 + mode) {
+    case 8 + 4: return admm_eval_kernel<1, 4>;
+    case 8 + 1: return admm_eval_kernel<1, 1>;
+    case 8 + 2: return admm_eval_kernel<1, 2>;
+    case 16 + 4: return admm_eval_kernel<2, 4>;
+    case 16 + 1: return admm_eval_kernel<2, 1>;
+    case 16 + 2: return admm_eval_kernel<2, 2>;
+    case 24 + 4: return admm_eval_kernel<3, 4>;
+    case 24 + 1: return admm_eval_kernel<3, 1>;
+    case 24 + 2: return admm_eval_kernel<3, 2>;
     }
     return nullptr;
 }
@@ -209,44 +209,24 @@ static int prepare(sqw_admm *h)
     D.NN = h->NN;
     D.npad = D.C * D.dimp;
     D.upad = D.E * D.dimp;
-    D.wstride = D.dimp;  // dimp = 8 (mod 16) doubles: rows alternate between the two 64-byte
-                         // halves of the 128-byte bank window, for X tiles and W alike
+    D.wstride = D.dimp;
     D.world = h->world;
     D.ridge = h->ridge;
     const int nct = D.Cp / 8;
-    if (nct > 3)
-        return set_error(SQW_ERR_UNSUPPORTED, "more than 24 leaf classes (%d) not supported yet", D.C);
     if ((long long)D.Cp * D.dimp * h->dev.T_local > (1ll << 31) - 1 || (long long)D.upad > (1 << 30))
         return set_error(SQW_ERR_UNSUPPORTED, "problem too large for 32-bit coordinate indices");
 
     cudaDeviceProp prop;
     SQW_CUDA_CHECK(cudaGetDeviceProperties(&prop, h->device));
     const int n_sm = prop.multiProcessorCount;
-    const size_t budget = (size_t)prop.sharedMemPerBlockOptin - 2048;  // static SolveSmem etc.
+    const int mode = h->eval_mode;
     const size_t w_bytes = (size_t)D.Cp * D.wstride * sizeof(double);
-    TileSmemLayout L = tile_smem_layout(D.Cp, D.dimp, budget, kSolveScratchBytes);
-    const int ngroups = (D.dimp + 15) / 16;
-    const int nbg = (nct <= 2) ? 6 : 4;
-    int mode;
-    if (L.NS >= 2 && ngroups <= kWarps * nbg)
-        mode = 0;
-    else if (w_bytes <= 160 * 1024)
-        mode = 1;
-    else
-        mode = 2;
-    if (const char *env = getenv("SQW_ADMM_EVAL_MODE")) {
-        const int m = atoi(env);
-        if (m >= mode && m <= 2)
-            mode = m;  // only towards the more general paths
-    }
-    h->eval_mode = mode;
-    if (mode == 0)
-        h->xupdate_smem = L.total;
+    if (mode == 4)
+        h->xupdate_smem = h->layout.total;
     else if (mode == 1)
         h->xupdate_smem = std::max(w_bytes, kSolveScratchBytes);
     else
         h->xupdate_smem = kSolveScratchBytes;
-    h->layout = L;
     XKernel xk = xupdate_kernel(nct, mode);
     EKernel ek = eval_kernel(nct, mode);
     SQW_CUDA_CHECK(cudaFuncSetAttribute(xk, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -309,7 +289,7 @@ static int prepare(sqw_admm *h)
     TRY(h->dalloc(&D.bar, TL * 32));
     TRY(h->dalloc(&D.nfev, TL));
     if (getenv("SQW_ADMM_PROFILE"))
-        TRY(h->dalloc(&D.prof, TL * D.G * 8));
+        TRY(h->dalloc(&D.prof, TL * D.G * 16));
     TRY(h->dalloc(&D.sum1, (size_t)D.npad + D.upad));
     TRY(h->dalloc(&D.sum2, (size_t)D.E));
     TRY(h->dalloc(&D.edge_stats, (size_t)D.E * 4));
@@ -371,7 +351,7 @@ static int enqueue_iteration(sqw_admm *h, int slot)
     admm_pack_kernel<<<(total + 255) / 256, 256, 0, h->stream>>>(D);
     if ((rc = nccl_allreduce(h, D.sum1, (size_t)total)) != SQW_OK)
         return rc;
-    admm_consensus_kernel<<<D.E, 256, 0, h->stream>>>(D);
+    admm_consensus_kernel<<<D.E, kThreads, 0, h->stream>>>(D);  // block_sum() needs kThreads
     if ((rc = nccl_allreduce(h, D.sum2, (size_t)D.E)) != SQW_OK)
         return rc;
     admm_decide_kernel<<<1, 32, 0, h->stream>>>(D);
@@ -601,10 +581,35 @@ static int plan_blocks(sqw_admm *h, int64_t n_rows, int32_t dim, int32_t num_cla
     D.T_local = (int)h->block_ids.size();
     D.nb = (int)(n_rows / h->T);
     D.dim = dim;
-    // padded row length: a multiple of 8 doubles with dimp/8 odd (see admm_eval_tma.cuh)
-    D.dimp = (dim + 7) / 8 * 8;
-    if (((D.dimp / 8) & 1) == 0)
-        D.dimp += 8;
+    // Evaluation mode and padded row length (admm_kernels.cuh, admm_eval_tma.cuh):
+    //   mode 4 (TMA tiles): dimp = 4 (mod 8) doubles; modes 1/2 (streaming): dimp = 8 (mod 16).
+    cudaDeviceProp prop;
+    SQW_CUDA_CHECK(cudaGetDeviceProperties(&prop, h->device));
+    const int Cp = (num_classes + 7) / 8 * 8, nct = Cp / 8;
+    if (nct > 3)
+        return set_error(SQW_ERR_UNSUPPORTED, "more than 24 leaf classes (%d) not supported yet",
+                         num_classes);
+    int dimp4 = (dim + 3) / 4 * 4;
+    if ((dimp4 & 7) == 0)
+        dimp4 += 4;
+    int dimp8 = (dim + 7) / 8 * 8;
+    if (((dimp8 / 8) & 1) == 0)
+        dimp8 += 8;
+    const size_t budget = (size_t)prop.sharedMemPerBlockOptin - 2048;  // static SolveSmem etc.
+    TileSmemLayout L = tile_smem_layout(Cp, dimp4, budget, kSolveScratchBytes);
+    const bool ws_ok = L.NS >= 3 && L.NS <= 4 && (dimp4 + 15) / 16 <= kDmmaWarps * 6 &&
+                       dimp4 / 4 <= kDmmaWarps * 24;
+    int mode = ws_ok ? 4 : ((size_t)Cp * dimp8 * 8 <= 160 * 1024 ? 1 : 2);
+    if (const char *env = getenv("SQW_ADMM_EVAL_MODE")) {  // test hook: force a more general path
+        const int m = atoi(env);
+        if (m == 1 && (size_t)Cp * dimp8 * 8 <= 160 * 1024)
+            mode = 1;
+        else if (m == 2)
+            mode = 2;
+    }
+    h->eval_mode = mode;
+    h->layout = L;
+    D.dimp = (mode == 4) ? dimp4 : dimp8;
     return SQW_OK;
 }
 
@@ -815,7 +820,7 @@ int sqw_admm_execute(sqw_admm *h, double *x_inout, double *smx_inout)
                                                     L.d_idx);
                 h->stats.launches += 1;
             }
-        admm_outer_check_kernel<<<D.NN, 256, 0, st>>>(D);
+        admm_outer_check_kernel<<<D.NN, kThreads, 0, st>>>(D);
         h->stats.launches += 1;
         Ctrl cc;
         SQW_CUDA_CHECK(cudaMemcpyAsync(&h->h_ring[0], D.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
@@ -841,14 +846,18 @@ int sqw_admm_execute(sqw_admm *h, double *x_inout, double *smx_inout)
     if ((rc = download_padded(h, D.smx, D.NN, D.dim, D.dimp, smx_inout)) != SQW_OK) return rc;
 
     if (D.prof) {
-        std::vector<long long> pr((size_t)D.T_local * D.G * 8);
+        std::vector<long long> pr((size_t)D.T_local * D.G * 16);
         SQW_CUDA_CHECK(cudaMemcpy(pr.data(), D.prof, pr.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         const char *names[7] = {"eval", "barrier1", "reduce", "barrier2", "decide", "update", "barrier3"};
         for (int c : {0, D.G / 2, D.G - 1}) {
-            const long long *q = &pr[(size_t)c * 8];
+            const long long *q = &pr[(size_t)c * 16];
             fprintf(stderr, "[sqw profile] block 0 cta %d: evals %lld;", c, q[7]);
             for (int i = 0; i < 7; ++i)
                 fprintf(stderr, " %s %.0f cyc", names[i], q[7] ? (double)q[i] / q[7] : 0.0);
+            const char *en[8] = {"Wstage", "tilewait", "pass1", "rr_wait", "-", "pass2", "free_arrive", "combine"};
+            fprintf(stderr, "\n[sqw profile]    eval breakdown per eval:");
+            for (int i = 0; i < 8; ++i)
+                fprintf(stderr, " %s %.0f", en[i], q[7] ? (double)q[8 + i] / q[7] : 0.0);
             fprintf(stderr, "\n");
         }
         SQW_CUDA_CHECK(cudaMemset(D.prof, 0, pr.size() * sizeof(long long)));
@@ -998,8 +1007,12 @@ int sqw_lbfgs_rosenbrock(int32_t n, double *x_inout, double eps, int32_t *nfev_o
     ws.prof = nullptr;
     SQW_CUDA_CHECK(cudaMemcpy(ws.x, x_inout, nv * sizeof(double), cudaMemcpyHostToDevice));
     void *args[] = {&ws, &bar, &eps, &out};
-    cudaError_t e = cudaLaunchCooperativeKernel((void *)lbfgs_rosenbrock_kernel, dim3(G),
-                                                dim3(kThreads), args, 0, 0);
+    cudaError_t e = cudaFuncSetAttribute(lbfgs_rosenbrock_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kSolveScratchBytes);
+    if (e == cudaSuccess)
+        e = cudaLaunchCooperativeKernel((void *)lbfgs_rosenbrock_kernel, dim3(G), dim3(kThreads), args,
+                                        kSolveScratchBytes, 0);
     if (e == cudaSuccess)
         e = cudaDeviceSynchronize();
     int res[2] = {0, 0};

@@ -1,21 +1,19 @@
 // admm_eval_tma.cuh — fused single-pass (objective, gradient) evaluation for row lengths that fit
-// shared memory: the fast path of the x-update kernel.
+// shared memory: the fast path of the x-update kernel (MODE 4).
 //
 // Same mathematics as admm_eval.cuh (LOne.java:1007-1029, 941-979); different data movement:
 //   * the CTA's rows travel HBM -> shared memory exactly once per evaluation as 8-row tiles moved
-//     by the TMA engine (cp.async.bulk, one bulk copy per tile: rows are contiguous in the
-//     block-major layout) into an NS-deep ring guarded by mbarriers; no thread ever waits on a
-//     global load, so eight warps per SM are enough to keep ~170 KB in flight;
-//   * both passes read the tile from shared memory with 16-byte LDS: pass 1 splits the K (column)
-//     range over the 8 warps (partial logits are summed through a 4 KB scratch), pass 2 splits
-//     the column groups over the warps with the gradient accumulators pinned in registers for
-//     the whole evaluation;
-//   * the ring keeps running across evaluations: while the solver's reduce / decide phases run,
-//     the first NS tiles of the next evaluation are already in flight; if the CTA's rows fit the
-//     ring entirely they are loaded once per kernel and every later evaluation runs from
-//     shared memory.
-// Row stride dimp is kept = 8 (mod 16) doubles so that the 8-row x 64-byte fragment reads of
-// pass 1 and the 8-class x 64-byte reads of W hit all 32 banks (4 wavefronts per LDS.128).
+//     by the TMA engine (cp.async.bulk, one bulk copy per row, eight on one mbarrier) into an
+//     NS-deep ring; no thread ever waits on a global load;
+//   * both passes read the tile from shared memory; the ring keeps running across evaluations:
+//     while the solver's reduce / decide phases run, the first NS tiles of the next evaluation
+//     are already in flight; if the CTA's rows fit the ring entirely they are loaded once per
+//     kernel and every later evaluation runs from shared memory.
+// Row stride: dimp = 4 (mod 8) doubles, i.e. 32 or 96 bytes (mod 128). Pass 1 reads 8 rows x 4
+// consecutive doubles per LDS.64 (half-warp = 4 rows x 32 B, offsets 0/32/64/96: conflict free),
+// pass 2 reads 4 rows x 8 x 16 B per LDS.128 (quarter-warp = 4 rows x 2 x 16 B: conflict free).
+// (A stride of 64 mod 128 serves pass 1 with LDS.128 but gives 2-way conflicts in pass 2:
+// measured 1.6k instead of 0.7k cycles per tile.)
 #pragma once
 
 #include "admm_eval.cuh"
@@ -67,14 +65,9 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
         : "memory");
 }
 
-template <int NCT>
-struct TileEvalCfg {
-    static constexpr int NBG = (NCT <= 2) ? 6 : 4;  // 16-column groups per warp held in registers
-};
-
 // Shared-memory carve-up of the x-update kernel (fast path); offsets in bytes.
 struct TileSmemLayout {
-    size_t w_off, w_bytes;         // W [Cp][dimp]; doubles as the reduce scratch of the solver
+    size_t w_off, w_bytes;         // W [Cp][dimp] (C > 8 only); doubles as the solver's reduce scratch
     size_t stage_off, stage_bytes; // NS stages of kTileRows x dimp doubles
     size_t plog_off;               // [kWarps][NCT][32] double2 partial logits
     size_t rs_off;                 // [kWarps][NCT][64] residual fragments
@@ -88,25 +81,62 @@ inline TileSmemLayout tile_smem_layout(int Cp, int dimp, size_t budget, size_t m
     TileSmemLayout L{};
     const int nct = Cp / 8;
     L.w_off = 0;
-    L.w_bytes = std::max((size_t)Cp * dimp * 8, min_w_bytes);
+    L.w_bytes = std::max(nct > 1 ? (size_t)Cp * dimp * 8 : (size_t)0, min_w_bytes);
     L.w_bytes = (L.w_bytes + 127) & ~(size_t)127;
     L.stage_bytes = (size_t)kTileRows * dimp * 8;
-    const size_t fixed = L.w_bytes + (size_t)kWarps * nct * 32 * 16 + (size_t)kWarps * nct * 64 * 8 + 128;
+    const size_t plog_bytes = (size_t)2 * kWarps * nct * 32 * 16;  // double-buffered partial logits
+    const size_t fixed = L.w_bytes + plog_bytes + (size_t)kWarps * nct * 64 * 8 + 128;
     int ns = 0;
     if (budget > fixed)
         ns = (int)std::min<size_t>(4, (budget - fixed) / L.stage_bytes);
     L.NS = ns;
     L.stage_off = L.w_bytes;
     L.plog_off = L.stage_off + (size_t)ns * L.stage_bytes;
-    L.rs_off = L.plog_off + (size_t)kWarps * nct * 32 * 16;
+    L.rs_off = L.plog_off + plog_bytes;
     L.bar_off = L.rs_off + (size_t)kWarps * nct * 64 * 8;
     L.total = L.bar_off + 128;
     return L;
 }
 
+}  // namespace sqw
+
+// ----------------------------------------------------------------------------------------------
+// Warp-specialised variant (MODE 4): 8 DMMA warps + 2 softmax warps + 1 TMA producer warp.
+//
+// Measured on B200 with the variants above (SQW_ADMM_PROFILE, cfg-2): of 72k cycles per
+// evaluation only 25k are DMMA issue; 15k sit in the softmax dependency chain (LDS -> max ->
+// exp -> sum -> div, fp64, ~1.7k cycles per tile, executed by every warp), 14k in waits for a
+// single 42 KB bulk copy per tile, the rest in barriers. Here
+//   * warps 0..7 only ever run DMMA sections: pass 1 of tile j, then pass 2 of tile j-1;
+//   * warps 8 / 9 turn the partial logits of the even / odd tiles into residual fragments while
+//     the DMMA warps are busy with the neighbouring tiles (double-buffered scratch, named
+//     barriers bar.arrive / bar.sync between the roles) and own the NLL sums; one softmax warp
+//     alone (~2k cycles of dependent fp64 exp / div / log per tile) would pace the whole pipeline;
+//   * every tile is fetched as 8 per-row bulk copies on one mbarrier, four tiles deep.
+namespace sqw {
+
+constexpr int kDmmaWarps = 8;     // warps 0..7 issue DMMA only: two per SM sub-partition (the DMMA
+                                  // pipe is per sub-partition, 16 cycles per m8n8k4)
+constexpr int kSoftmaxWarps = 2;  // warps 8, 9: softmax of the even / odd tiles
+constexpr int kProducerWarp = 10; // lane 0 re-fills released stages (TMA issue costs ~140 cycles
+                                  // per bulk copy: kept off the DMMA warps)
+
+__device__ __forceinline__ void nbar_sync(int id, int threads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void nbar_arrive(int id, int threads)
+{
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+struct WsSmemLayout {
+    static constexpr int kBarPl = 1, kBarRr = 3, kBarFree = 5;  // kBarFree + stage (<= 4 stages)
+};
+
 template <int NCT>
-struct TileEval {
-    static constexpr int NBG = TileEvalCfg<NCT>::NBG;
+struct TileEvalWS {
+    static constexpr int NBG = 6;  // 16-column groups per DMMA warp: rows up to 8*6*16 = 768 columns
     const AdmmDev &P;
     int blk, cta;
     double *smW, *stages, *rs;
@@ -115,38 +145,42 @@ struct TileEval {
     double *red;
     int NS, r0, r1, ntiles;
     bool resident;
-    long long q;       // sequence number of the next tile to consume (streaming mode)
+    int cs, cph;   // streaming mode: stage / mbarrier parity of the next tile to consume
+    int pt;        // streaming mode (producer lane): next tile index to fetch
     int evals_done;
     const double *Xb;
+    long long *prof;
 
-    __device__ void issue(long long qq)
+    // fetch tile `tile` of this CTA into stage s: one bulk copy per row, all on full[s]
+    __device__ void issue(int tile, int s)
     {
-        const int tile = (int)(qq % ntiles), s = (int)(qq % NS);
         const int row = r0 + tile * kTileRows;
         const int rows = min(kTileRows, r1 - row);
-        const unsigned bytes = (unsigned)rows * (unsigned)P.dimp * 8u;
-        mbar_expect_tx(&full[s], bytes);
-        bulk_g2s(stages + (size_t)s * kTileRows * P.dimp, Xb + (size_t)row * P.dimp, bytes, &full[s]);
+        const unsigned row_bytes = (unsigned)P.dimp * 8u;
+        mbar_expect_tx(&full[s], (unsigned)rows * row_bytes);
+        double *dst = stages + (size_t)s * kTileRows * P.dimp;
+        const double *src = Xb + (size_t)row * P.dimp;
+        for (int r = 0; r < rows; ++r)
+            bulk_g2s(dst + (size_t)r * P.dimp, src + (size_t)r * P.dimp, row_bytes, &full[s]);
     }
 
     __device__ void init(unsigned char *smem, const TileSmemLayout &L, double *red_)
     {
         smW = reinterpret_cast<double *>(smem + L.w_off);
         stages = reinterpret_cast<double *>(smem + L.stage_off);
-        plog = reinterpret_cast<double2 *>(smem + L.plog_off);
-        rs = reinterpret_cast<double *>(smem + L.rs_off);
+        plog = reinterpret_cast<double2 *>(smem + L.plog_off);   // [2][7][NCT][32]
+        rs = reinterpret_cast<double *>(smem + L.rs_off);        // [2][NCT][64]
         full = reinterpret_cast<unsigned long long *>(smem + L.bar_off);
         red = red_;
         NS = L.NS;
         cta_row_range(P, cta, r0, r1);
-        ntiles = (r1 - r0 + kTileRows - 1) / kTileRows;
-        if (ntiles < 0)
-            ntiles = 0;
+        ntiles = max(0, (r1 - r0 + kTileRows - 1) / kTileRows);
         resident = ntiles <= NS;
-        q = 0;
+        cs = cph = 0;
+        pt = 0;
         evals_done = 0;
+        prof = P.prof ? P.prof + (size_t)blockIdx.x * 16 + 8 : nullptr;
         Xb = P.X + (size_t)blk * P.nb * P.dimp;
-        // stale rows of a partially filled stage must stay finite (0 * NaN would poison pass 2)
         for (size_t i = threadIdx.x; i < (size_t)NS * kTileRows * P.dimp; i += kThreads)
             stages[i] = 0.0;
         if (threadIdx.x == 0) {
@@ -155,28 +189,58 @@ struct TileEval {
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // zero fill before TMA writes
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
-        if (threadIdx.x == 0 && ntiles > 0) {
+        if (threadIdx.x == kProducerWarp * 32 && ntiles > 0) {
             const int first = resident ? ntiles : NS;
             for (int i = 0; i < first; ++i)
-                issue(i);
+                issue(i, i);     // not resident: ntiles > NS, so tile i exists
+            pt = resident ? 0 : (NS == ntiles ? 0 : NS);
         }
     }
 
-    // Outstanding bulk copies must land before the CTA may exit.
     __device__ void drain()
     {
-        if (ntiles == 0 || resident) {
-            if (resident && evals_done == 0)
+        if (ntiles == 0)
+            return;
+        if (resident) {
+            if (evals_done == 0)
                 for (int s = 0; s < ntiles; ++s)
                     mbar_wait(&full[s], 0);
             return;
         }
+        int s = cs, ph = cph;
         for (int i = 0; i < NS; ++i) {
-            const long long qq = q + i;
-            mbar_wait(&full[qq % NS], (unsigned)((qq / NS) & 1));
+            mbar_wait(&full[s], (unsigned)ph);
+            if (++s == NS) {
+                s = 0;
+                ph ^= 1;
+            }
         }
+    }
+
+    // wait for the next tile of the sequence; returns its stage
+    __device__ __forceinline__ int stage_wait(int j)
+    {
+        if (resident) {
+            if (evals_done == 0)
+                mbar_wait(&full[j], 0);
+            return j;
+        }
+        const int s = cs;
+        mbar_wait(&full[s], (unsigned)cph);
+        if (++cs == NS) {
+            cs = 0;
+            cph ^= 1;
+        }
+        return s;
+    }
+    // re-fill the stage that tile processing just released (producer lane only)
+    __device__ __forceinline__ void refill(int s)
+    {
+        issue(pt, s);
+        if (++pt == ntiles)
+            pt = 0;
     }
 
     __device__ double eval(const double *xcur)
@@ -184,17 +248,28 @@ struct TileEval {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         const int qd = lane & 3, gid = lane >> 2;
         const int dimp = P.dimp, Cp = P.Cp;
-        // W -> shared memory (rows >= C are zero)
-        for (int i = threadIdx.x; i < Cp * dimp; i += kThreads)
-            smW[i] = (i < P.npad) ? __ldcg(xcur + i) : 0.0;
-        __syncthreads();
+        long long tk0 = 0, tk1 = 0;
+        const bool do_prof = prof != nullptr && threadIdx.x == 0;
+        if (do_prof)
+            tk0 = clock64();
+#define SQW_EPROF(slot)          \
+    if (do_prof) {               \
+        tk1 = clock64();         \
+        prof[slot] += tk1 - tk0; \
+        tk0 = tk1;               \
+    }
+        constexpr bool W_REG = (NCT == 1);  // one class tile: this warp's W fragments live in registers
+        constexpr int KSW = 24;             // k-steps (4 columns) per DMMA warp: dimp <= 8*24*4 = 768
+        if (!W_REG) {
+            for (int i = threadIdx.x; i < Cp * dimp; i += kThreads)
+                smW[i] = (i < P.npad) ? __ldcg(xcur + i) : 0.0;
+            __syncthreads();
+        }
+        SQW_EPROF(0)
 
-        const int nkp = dimp >> 3;
-        const int kp0 = nkp * warp / kWarps, kp1 = nkp * (warp + 1) / kWarps;
+        const int nks = dimp >> 2;
         const int ngroups = (dimp + 15) >> 4;
-        const int *yb = P.y + (size_t)blk * P.nb;
-        const double *wb = P.w + (size_t)blk * P.nb;
-
+        double facc = 0.0;
         double acc[NBG][2][NCT][2];
 #pragma unroll
         for (int i = 0; i < NBG; ++i)
@@ -203,157 +278,227 @@ struct TileEval {
 #pragma unroll
                 for (int ct = 0; ct < NCT; ++ct)
                     acc[i][h][ct][0] = acc[i][h][ct][1] = 0.0;
-        double facc = 0.0;
 
-        for (int t = 0; t < ntiles; ++t) {
-            int s;
-            if (resident) {
-                s = t;
-                if (evals_done == 0)
-                    mbar_wait(&full[s], 0);
-            } else {
-                const long long qq = q + t;
-                s = (int)(qq % NS);
-                mbar_wait(&full[s], (unsigned)((qq / NS) & 1));
-            }
-            const double *tile = stages + (size_t)s * kTileRows * dimp;
-
-            // ---- pass 1: partial logits of the 8 rows over this warp's k range
-            {
-                double pa[NCT][2][2];
+        if (warp < kDmmaWarps) {
+            // =========================== DMMA warps ===========================
+            const int ks0 = nks * warp / kDmmaWarps, ks1 = nks * (warp + 1) / kDmmaWarps;
+            double wreg[W_REG ? KSW : 1];
+            if (W_REG) {
+                // W[class gid][4 ks + qd] straight from the global trial point (L2)
+                const double *wg = xcur + (size_t)gid * dimp + qd;
 #pragma unroll
-                for (int ct = 0; ct < NCT; ++ct)
-                    pa[ct][0][0] = pa[ct][0][1] = pa[ct][1][0] = pa[ct][1][1] = 0.0;
-                const double2 *xp = reinterpret_cast<const double2 *>(tile + (size_t)gid * dimp) + qd;
-                const double2 *wp = reinterpret_cast<const double2 *>(smW + (size_t)gid * dimp) + qd;
-#pragma unroll 4
-                for (int kp = kp0; kp < kp1; ++kp) {
-                    const double2 xa = xp[4 * kp];
+                for (int u = 0; u < KSW; ++u) {
+                    wreg[u] = 0.0;
+                    if (ks0 + u < ks1 && gid < P.C)
+                        wreg[u] = __ldcg(wg + 4 * (ks0 + u));
+                }
+            }
+            auto pass2 = [&](int j, int sj) {
+                const double *tile = stages + (size_t)sj * kTileRows * dimp;
+                const double *myrs = rs + (size_t)(j & 1) * NCT * 64;
+                double a[NCT][2];
+#pragma unroll
+                for (int ct = 0; ct < NCT; ++ct) {
+                    a[ct][0] = myrs[ct * 64 + qd * 8 + gid];        // R[row qd][class gid]
+                    a[ct][1] = myrs[ct * 64 + (4 + qd) * 8 + gid];  // R[row 4+qd][class gid]
+                }
+                // straight-line code: out-of-range column groups / columns read a valid address and
+                // are multiplied by zero, so every LDS can be scheduled ahead of the DMMAs
+                double2 x0[NBG], x1[NBG];
+#pragma unroll
+                for (int i = 0; i < NBG; ++i) {
+                    const int col = 16 * (warp + kDmmaWarps * i) + 2 * gid;
+                    const int colc = (col < dimp) ? col : 0;
+                    x0[i] = *reinterpret_cast<const double2 *>(tile + (size_t)qd * dimp + colc);
+                    x1[i] = *reinterpret_cast<const double2 *>(tile + (size_t)(4 + qd) * dimp + colc);
+                    if (col >= dimp)
+                        x0[i] = x1[i] = make_double2(0.0, 0.0);
+                }
+#pragma unroll
+                for (int i = 0; i < NBG; ++i) {
 #pragma unroll
                     for (int ct = 0; ct < NCT; ++ct) {
-                        const double2 wv = wp[(size_t)ct * 4 * dimp + 4 * kp];
-                        dmma884(pa[ct][0], xa.x, wv.x);
-                        dmma884(pa[ct][1], xa.y, wv.y);
+                        dmma884(acc[i][0][ct], a[ct][0], x0[i].x);
+                        dmma884(acc[i][1][ct], a[ct][0], x0[i].y);
+                        dmma884(acc[i][0][ct], a[ct][1], x1[i].x);
+                        dmma884(acc[i][1][ct], a[ct][1], x1[i].y);
                     }
                 }
+            };
+            int sprev = 0;
+            for (int j = 0; j < ntiles; ++j) {
+                const int s = stage_wait(j);
+                SQW_EPROF(1)
+                const double *tile = stages + (size_t)s * kTileRows * dimp;
+                {   // pass 1: partial logits over this warp's k range, 4 DMMA chains per class tile
+                    double pa[NCT][4][2];
+#pragma unroll
+                    for (int ct = 0; ct < NCT; ++ct)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            pa[ct][c][0] = pa[ct][c][1] = 0.0;
+                    const double *xp = tile + (size_t)gid * dimp + qd;
+                    if (W_REG) {
+                        double xa[KSW];  // wreg[u] is zero beyond ks1: clamped loads need no select
+#pragma unroll
+                        for (int u = 0; u < KSW; ++u)
+                            xa[u] = xp[4 * min(ks0 + u, ks1 - 1)];
+#pragma unroll
+                        for (int u = 0; u < KSW; ++u)
+                            dmma884(pa[0][u & 3], xa[u], wreg[u]);
+                    } else {
+                        const double *wp = smW + (size_t)gid * dimp + qd;
+#pragma unroll 4
+                        for (int ks = ks0; ks < ks1; ++ks) {
+                            const double xa = xp[4 * ks];
+#pragma unroll
+                            for (int ct = 0; ct < NCT; ++ct)
+                                dmma884(pa[ct][ks & 3], xa, wp[(size_t)ct * 8 * dimp + 4 * ks]);
+                        }
+                    }
+                    double2 *dst = plog + ((size_t)(j & 1) * kDmmaWarps + warp) * NCT * 32;
+#pragma unroll
+                    for (int ct = 0; ct < NCT; ++ct)
+                        dst[ct * 32 + lane] =
+                            make_double2((pa[ct][0][0] + pa[ct][1][0]) + (pa[ct][2][0] + pa[ct][3][0]),
+                                         (pa[ct][0][1] + pa[ct][1][1]) + (pa[ct][2][1] + pa[ct][3][1]));
+                }
+                SQW_EPROF(2)
+                nbar_arrive(WsSmemLayout::kBarPl + (j & 1), (kDmmaWarps + 1) * 32);  // partial logits of tile j ready
+                if (j >= 1) {
+                    nbar_sync(WsSmemLayout::kBarRr + ((j - 1) & 1), (kDmmaWarps + 1) * 32);  // residuals of tile j-1
+                    SQW_EPROF(3)
+                    pass2(j - 1, sprev);
+                    SQW_EPROF(5)
+                    if (!resident)  // tell the producer warp that the stage of tile j-1 is free
+                        nbar_arrive(WsSmemLayout::kBarFree + sprev, (kDmmaWarps + 1) * 32);
+                    SQW_EPROF(6)
+                }
+                sprev = s;
+            }
+            if (ntiles > 0) {
+                nbar_sync(WsSmemLayout::kBarRr + ((ntiles - 1) & 1), (kDmmaWarps + 1) * 32);
+                SQW_EPROF(3)
+                pass2(ntiles - 1, sprev);
+                SQW_EPROF(5)
+                if (!resident)
+                    nbar_arrive(WsSmemLayout::kBarFree + sprev, (kDmmaWarps + 1) * 32);
+                SQW_EPROF(6)
+            }
+        } else if (warp == kProducerWarp) {
+            // =========================== TMA producer ===========================
+            if (!resident) {
+                int s = cs;
+                for (int j = 0; j < ntiles; ++j) {
+                    nbar_sync(WsSmemLayout::kBarFree + s, (kDmmaWarps + 1) * 32);
+                    if (lane == 0)
+                        refill(s);
+                    if (++s == NS)
+                        s = 0;
+                }
+            }
+        } else if (warp < kDmmaWarps + kSoftmaxWarps) {
+            // =========================== softmax warp ===========================
+            const int *yb = P.y + (size_t)blk * P.nb;
+            const double *wb = P.w + (size_t)blk * P.nb;
+            for (int j = warp - kDmmaWarps; j < ntiles; j += kSoftmaxWarps) {
+                const int row = r0 + j * kTileRows + gid;
+                const bool rv = row < r1;
+                const int rowc = rv ? row : r0;
+                const int cls = yb[rowc];
+                const double wi = wb[rowc];
+                nbar_sync(WsSmemLayout::kBarPl + (j & 1), (kDmmaWarps + 1) * 32);
+                const double2 *src = plog + (size_t)(j & 1) * kDmmaWarps * NCT * 32;
+                double sv[NCT][2];
+                double mx = -INFINITY;
+#pragma unroll
+                for (int ct = 0; ct < NCT; ++ct) {
+                    double2 v = src[ct * 32 + lane];
+#pragma unroll
+                    for (int w7 = 1; w7 < kDmmaWarps; ++w7) {
+                        const double2 pv = src[(w7 * NCT + ct) * 32 + lane];
+                        v.x += pv.x;
+                        v.y += pv.y;
+                    }
+                    sv[ct][0] = v.x;
+                    sv[ct][1] = v.y;
+                    if (ct * 8 + 2 * qd < P.C)
+                        mx = fmax(mx, v.x);
+                    if (ct * 8 + 2 * qd + 1 < P.C)
+                        mx = fmax(mx, v.y);
+                }
+                mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                double ex[NCT][2], den = 0.0;
 #pragma unroll
                 for (int ct = 0; ct < NCT; ++ct)
-                    plog[(warp * NCT + ct) * 32 + lane] =
-                        make_double2(pa[ct][0][0] + pa[ct][1][0], pa[ct][0][1] + pa[ct][1][1]);
-            }
-            __syncthreads();
-
-            // ---- logits -> softmax -> residual fragments (every warp, redundantly)
-            const int row = r0 + t * kTileRows + gid;
-            const bool rv = row < r1;
-            const int rowc = rv ? row : r0;
-            double sv[NCT][2];
-            double mx = -INFINITY;
 #pragma unroll
-            for (int ct = 0; ct < NCT; ++ct) {
-                double2 v = make_double2(0.0, 0.0);
-#pragma unroll
-                for (int w8 = 0; w8 < kWarps; ++w8) {
-                    const double2 pv = plog[(w8 * NCT + ct) * 32 + lane];
-                    v.x += pv.x;
-                    v.y += pv.y;
-                }
-                sv[ct][0] = v.x;
-                sv[ct][1] = v.y;
-                if (ct * 8 + 2 * qd < P.C)
-                    mx = fmax(mx, v.x);
-                if (ct * 8 + 2 * qd + 1 < P.C)
-                    mx = fmax(mx, v.y);
-            }
-            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-            double ex[NCT][2], den = 0.0;
-#pragma unroll
-            for (int ct = 0; ct < NCT; ++ct)
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    ex[ct][j] = (ct * 8 + 2 * qd + j < P.C) ? exp(sv[ct][j] - mx) : 0.0;
-                    den += ex[ct][j];
-                }
-            den += __shfl_xor_sync(0xffffffffu, den, 1);
-            den += __shfl_xor_sync(0xffffffffu, den, 2);
-            const int cls = yb[rowc];
-            const double wi = wb[rowc];
-            const double logden = log(den);
-            double *myrs = rs + (size_t)warp * NCT * 64;
-#pragma unroll
-            for (int ct = 0; ct < NCT; ++ct) {
-                double rr[2];
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int c = ct * 8 + 2 * qd + j;
-                    double r = wi * (ex[ct][j] / den);
-                    if (c == cls) {
-                        r -= wi;
-                        if (rv && warp == 0)
-                            facc -= wi * ((sv[ct][j] - mx) - logden);
+                    for (int jj = 0; jj < 2; ++jj) {
+                        ex[ct][jj] = (ct * 8 + 2 * qd + jj < P.C) ? exp(sv[ct][jj] - mx) : 0.0;
+                        den += ex[ct][jj];
                     }
-                    rr[j] = rv ? r : 0.0;
-                }
-                *reinterpret_cast<double2 *>(myrs + ct * 64 + gid * 8 + 2 * qd) =
-                    make_double2(rr[0], rr[1]);
-            }
-            __syncwarp();
-            double a[NCT][2];
+                den += __shfl_xor_sync(0xffffffffu, den, 1);
+                den += __shfl_xor_sync(0xffffffffu, den, 2);
+                double *myrs = rs + (size_t)(j & 1) * NCT * 64;
 #pragma unroll
-            for (int ct = 0; ct < NCT; ++ct) {
-                a[ct][0] = myrs[ct * 64 + qd * 8 + gid];        // R[row qd][class gid]
-                a[ct][1] = myrs[ct * 64 + (4 + qd) * 8 + gid];  // R[row 4+qd][class gid]
+                for (int ct = 0; ct < NCT; ++ct) {
+                    double rr[2];
+#pragma unroll
+                    for (int jj = 0; jj < 2; ++jj) {
+                        const int c = ct * 8 + 2 * qd + jj;
+                        double r = wi * (ex[ct][jj] / den);
+                        if (c == cls)
+                            r -= wi;
+                        rr[jj] = rv ? r : 0.0;
+                    }
+                    *reinterpret_cast<double2 *>(myrs + ct * 64 + gid * 8 + 2 * qd) =
+                        make_double2(rr[0], rr[1]);
+                }
+                __syncwarp();
+                nbar_arrive(WsSmemLayout::kBarRr + (j & 1), (kDmmaWarps + 1) * 32);
+                // the NLL term is off the critical path: after the residuals are published
+                const double logden = log(den);
+#pragma unroll
+                for (int ct = 0; ct < NCT; ++ct)
+#pragma unroll
+                    for (int jj = 0; jj < 2; ++jj)
+                        if (rv && ct * 8 + 2 * qd + jj == cls)
+                            facc -= wi * ((sv[ct][jj] - mx) - logden);
             }
-            __syncwarp();
+        }
+        if (!resident && warp >= kDmmaWarps) {
+            // only the DMMA warps wait on stages; keep everybody's copy of the ring position in step
+            const int adv = cs + ntiles;
+            cph ^= (adv / NS) & 1;
+            cs = adv % NS;
+        }
+        evals_done++;
+        __syncthreads();
 
-            // ---- pass 2: G[:, my column groups] += R^T X
+        // ---- partial gradient of this CTA
+        if (warp < kDmmaWarps) {
+            double *gp = P.gpart + ((size_t)blk * P.G + cta) * P.npad;
 #pragma unroll
             for (int i = 0; i < NBG; ++i) {
-                const int grp = warp + kWarps * i;
-                if (grp < ngroups) {
-                    const int col = 16 * grp + 2 * gid;
-                    const bool cok = col < dimp;
+                const int cg = warp + kDmmaWarps * i;
+                const int col = 16 * cg + 4 * qd;
+                if (cg < ngroups && col < dimp) {
 #pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) {
-                        double2 xb = make_double2(0.0, 0.0);
-                        if (cok)
-                            xb = *reinterpret_cast<const double2 *>(tile + (size_t)(4 * ks + qd) * dimp + col);
-#pragma unroll
-                        for (int ct = 0; ct < NCT; ++ct) {
-                            dmma884(acc[i][0][ct], a[ct][ks], xb.x);
-                            dmma884(acc[i][1][ct], a[ct][ks], xb.y);
+                    for (int ct = 0; ct < NCT; ++ct) {
+                        const int c = ct * 8 + gid;
+                        if (c < P.C) {
+                            double2 *dst = reinterpret_cast<double2 *>(gp + (size_t)c * dimp + col);
+                            __stcg(dst, make_double2(acc[i][0][ct][0], acc[i][1][ct][0]));
+                            __stcg(dst + 1, make_double2(acc[i][0][ct][1], acc[i][1][ct][1]));
                         }
                     }
                 }
             }
-            __syncthreads();  // every warp is done with this stage and with plog
-            if (!resident && threadIdx.x == 0)
-                issue(q + t + NS);
         }
-        if (!resident)
-            q += ntiles;
-        evals_done++;
-
-        // ---- partial gradient of this CTA
-        double *gp = P.gpart + ((size_t)blk * P.G + cta) * P.npad;
-#pragma unroll
-        for (int i = 0; i < NBG; ++i) {
-            const int grp = warp + kWarps * i;
-            const int col = 16 * grp + 4 * qd;
-            if (grp < ngroups && col < dimp) {
-#pragma unroll
-                for (int ct = 0; ct < NCT; ++ct) {
-                    const int c = ct * 8 + gid;
-                    if (c < P.C) {
-                        double2 *dst = reinterpret_cast<double2 *>(gp + (size_t)c * dimp + col);
-                        __stcg(dst, make_double2(acc[i][0][ct][0], acc[i][1][ct][0]));
-                        __stcg(dst + 1, make_double2(acc[i][0][ct][1], acc[i][1][ct][1]));
-                    }
-                }
-            }
-        }
-        return block_sum(facc, red);
+        const double fs = block_sum(facc, red);
+        SQW_EPROF(7)
+#undef SQW_EPROF
+        return fs;
     }
 };
 

@@ -33,53 +33,72 @@ __device__ __forceinline__ int ld_volatile_int(const int *p)
 
 // ------------------------------------------------------------------ x-update
 // Evaluation modes of the x-update kernel:
-//   MODE 0  fused single pass over TMA-staged 8-row tiles (admm_eval_tma.cuh): rows up to ~768
-//           columns, i.e. k = 4..5 feature sets;
+//   MODE 4  fused single pass over TMA-staged 8-row tiles, warp specialised (TileEvalWS):
+//           rows up to 672 columns, i.e. the k = 4..5 feature sets of the headline configs;
 //   MODE 1  two streaming passes from global memory, W in shared memory (admm_eval.cuh);
 //   MODE 2  the same with W read from global memory (row lengths beyond shared memory).
 template <int NCT, int MODE>
+struct StreamEval {
+    const AdmmDev &P;
+    int blk, cta;
+    double *smW, *red;
+    __device__ void init(unsigned char *smem, const TileSmemLayout &, double *red_)
+    {
+        smW = reinterpret_cast<double *>(smem);
+        red = red_;
+    }
+    __device__ double eval(const double *x)
+    {
+        return eval_data_term<NCT, MODE == 1>(P, blk, cta, x, smW, red);
+    }
+    __device__ void drain() {}
+};
+
+template <int NCT, int MODE>
+struct EvalSelect {
+    typedef StreamEval<NCT, MODE> type;
+};
+template <int NCT>
+struct EvalSelect<NCT, 4> {
+    typedef TileEvalWS<NCT> type;
+};
+
+template <class Eval>
 struct BlockProblem {
     const AdmmDev &P;
     int blk, cta;
-    double *smW;
-    double *red;
     double pho;
     const double *ut;
-    TileEval<NCT> *tile;
+    Eval &ev;
 
-    __device__ double eval_partial(const double *x)
-    {
-        if (MODE == 0)
-            return tile->eval(x);
-        return eval_data_term<NCT, MODE == 1>(P, blk, cta, x, smW, red);
-    }
+    __device__ double eval_partial(const double *x) { return ev.eval(x); }
 
     // gradient of coordinate k: data term reduced over the group's partials (fixed order), plus
     // the augmented Lagrangian term rho*(x - sm_x[par] - z + u_t) for w >= 1 (LOne.java:982-998);
-    // faug accumulates rho/2 * (...)^2 (LOne.java:1031-1047).
-    __device__ double grad_coord(int k, const double *x, double &faug)
+    // faug accumulates rho/2 * (...)^2 (LOne.java:1031-1047). xk = x[k].
+    __device__ double grad_coord(int k, double xk, double &faug)
     {
         const double *gp = P.gpart + (size_t)blk * P.G * P.npad + k;
         double s = 0.0;
-        for (int c0 = 0; c0 < P.G; c0 += 8) {
-            double v[8];
+        for (int c0 = 0; c0 < P.G; c0 += 32) {
+            double v[32];
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
+            for (int j = 0; j < 32; ++j)
                 v[j] = (c0 + j < P.G) ? __ldcg(gp + (size_t)(c0 + j) * P.npad) : 0.0;
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
+            for (int j = 0; j < 32; ++j)
                 s += v[j];
         }
         const int leaf = k / P.dimp, w = k - leaf * P.dimp;
         if (w >= 1 && w < P.dim) {
-            const double xk = __ldcg(x + k);
-            for (int e = P.leaf_edge_ptr[leaf]; e < P.leaf_edge_ptr[leaf + 1]; ++e) {
-                const int par = P.edge_par[e];
+            const int e0 = __ldg(P.leaf_edge_ptr + leaf), e1 = __ldg(P.leaf_edge_ptr + leaf + 1);
+            for (int e = e0; e < e1; ++e) {
+                const int par = __ldg(P.edge_par + e);
                 const size_t o = (size_t)e * P.dimp + w;
                 double v = xk;
                 if (par >= 0)
-                    v -= P.smx[(size_t)par * P.dimp + w];
-                v = (v - P.z[o]) + __ldcg(ut + o);
+                    v -= __ldg(P.smx + (size_t)par * P.dimp + w);
+                v = (v - __ldg(P.z + o)) + __ldcg(ut + o);
                 s += pho * v;
                 faug += (pho / 2) * v * v;
             }
@@ -100,9 +119,9 @@ __global__ void __launch_bounds__(kThreads, 1) admm_xupdate_kernel(AdmmDev P, Ti
     double *xt = P.xt + (size_t)blk * P.Cp * P.dimp;
     double *ut = P.ut + (size_t)blk * P.upad;
     sm.scratch = reinterpret_cast<double *>(smem_raw);
-    TileEval<NCT> tile{P, blk, cta};
-    if (MODE == 0)
-        tile.init(smem_raw, L, sm.red);
+    typedef typename EvalSelect<NCT, MODE>::type Eval;
+    Eval ev{P, blk, cta};
+    ev.init(smem_raw, L, sm.red);
 
     // u-update (LOne.java:833-861): x-hat_t = a x_t + (1-a) z_old - a sm_x[par];
     // u_t += x-hat_t - z; u_t /= rho_fold.  Slice of the edge coordinates per CTA.
@@ -123,7 +142,7 @@ __global__ void __launch_bounds__(kThreads, 1) admm_xupdate_kernel(AdmmDev P, Ti
     }
 
     GroupBarrier gb{P.bar + blk * 32, 0u, P.G};
-    BlockProblem<NCT, MODE> prob{P, blk, cta, reinterpret_cast<double *>(smem_raw), sm.red, pho, ut, &tile};
+    BlockProblem<Eval> prob{P, blk, cta, pho, ut, ev};
     SolveWs ws;
     ws.n = P.npad;
     ws.x = xt;
@@ -136,11 +155,10 @@ __global__ void __launch_bounds__(kThreads, 1) admm_xupdate_kernel(AdmmDev P, Ti
     ws.spart = P.spart + (size_t)blk * P.G * kNumDots;
     ws.G = P.G;
     ws.cta = cta;
-    ws.prof = P.prof ? P.prof + (size_t)blockIdx.x * 8 : nullptr;
+    ws.prof = P.prof ? P.prof + (size_t)blockIdx.x * 16 : nullptr;
     int status = 0;
     const int evals = lbfgs_group_solve(prob, ws, gb, sm, 0.1, 10e-16, status);  // LOne.java:874-875
-    if (MODE == 0)
-        tile.drain();
+    ev.drain();
     if (cta == 0 && threadIdx.x == 0) {
         P.nfev[blk] = evals;
         if (status == 1)
@@ -173,7 +191,7 @@ __global__ void __launch_bounds__(256) admm_pack_kernel(AdmmDev P)
 // LOne.java:670-716 restricted to edge e = (leaf, par): z_old <- z, x-bar, u-bar, x-hat, z,
 // soft-threshold with kappa = 2 lambda / (rho T) (intercept included), znorm (from u for a self
 // edge, :504), xnorm, dual residual term, and this rank's part of the primal residual term.
-__global__ void __launch_bounds__(256) admm_consensus_kernel(AdmmDev P)
+__global__ void __launch_bounds__(kThreads) admm_consensus_kernel(AdmmDev P)
 {
     __shared__ double red[kWarps];
     if (ld_volatile_int(&P.ctrl->done) || ld_volatile_int(&P.ctrl->fatal))
@@ -378,7 +396,7 @@ admm_update_layer_kernel(AdmmDev P, const int *nodes, int n_nodes, const int *nb
 }
 
 // LOne.java:152-174: per node delta = ||sm_x_old - sm_x||, target = NODES_tol * ||sm_x||.
-__global__ void __launch_bounds__(256) admm_outer_check_kernel(AdmmDev P)
+__global__ void __launch_bounds__(kThreads) admm_outer_check_kernel(AdmmDev P)
 {
     __shared__ double red[kWarps];
     const int node = blockIdx.x;
@@ -433,26 +451,28 @@ admm_eval_kernel(AdmmDev P, TileSmemLayout L, double pho, double *f_out)
     const int blk = blockIdx.x / P.G, cta = blockIdx.x - blk * P.G;
     double *xt = P.xt + (size_t)blk * P.Cp * P.dimp;
     GroupBarrier gb{P.bar + blk * 32, 0u, P.G};
-    TileEval<NCT> tile{P, blk, cta};
-    if (MODE == 0)
-        tile.init(smem_raw, L, sm.red);
-    BlockProblem<NCT, MODE> prob{P, blk, cta, reinterpret_cast<double *>(smem_raw), sm.red, pho,
-                                 P.ut + (size_t)blk * P.upad, &tile};
+    typedef typename EvalSelect<NCT, MODE>::type Eval;
+    Eval ev{P, blk, cta};
+    ev.init(smem_raw, L, sm.red);
+    BlockProblem<Eval> prob{P, blk, cta, pho, P.ut + (size_t)blk * P.upad, ev};
     double fpart = prob.eval_partial(xt);
-    if (MODE == 0) {
-        // second evaluation exercises the ring wrap-around / resident path; results must agree
-        const double f2 = prob.eval_partial(xt);
-        if (f2 != fpart)
-            fpart = nan("");
-        tile.drain();
+    if (MODE == 4) {
+        // further evaluations exercise the ring wrap-around / resident path; results must agree
+        for (int rep = 0; rep < 2; ++rep) {
+            __syncthreads();
+            const double f2 = prob.eval_partial(xt);
+            if (f2 != fpart)
+                fpart = nan("");
+        }
     }
+    ev.drain();
     gb.sync();
     const int n = P.npad;
     const int sl = ((n + P.G - 1) / P.G + 15) & ~15;
     const int k0 = min(n, cta * sl), k1 = min(n, k0 + sl);
     double faug = 0.0;
     for (int k = k0 + threadIdx.x; k < k1; k += kThreads)
-        P.g[(size_t)blk * n + k] = prob.grad_coord(k, xt, faug);
+        P.g[(size_t)blk * n + k] = prob.grad_coord(k, __ldcg(xt + k), faug);
     const double fa = block_sum(faug, sm.red);
     if (threadIdx.x == 0)
         atomicAdd(f_out + blk, fpart + fa);
@@ -461,7 +481,8 @@ admm_eval_kernel(AdmmDev P, TileSmemLayout L, double pho, double *f_out)
 struct RosenProblem {
     int n;
     __device__ double eval_partial(const double *) { return 0.0; }
-    __device__ double grad_coord(int k, const double *x, double &facc)
+    const double *x;
+    __device__ double grad_coord(int k, double, double &facc)
     {
         const int i = k >> 1;
         const double a = __ldcg(x + 2 * i), b = __ldcg(x + 2 * i + 1);
@@ -478,9 +499,9 @@ __global__ void __launch_bounds__(kThreads, 1)
 lbfgs_rosenbrock_kernel(SolveWs ws, unsigned *bar, double eps, int *out)
 {
     __shared__ SolveSmem sm;
-    __shared__ double scratch[kNumDots * (kThreads / 2)];
-    sm.scratch = scratch;
-    RosenProblem prob{ws.n};
+    extern __shared__ __align__(16) double rosen_scratch[];
+    sm.scratch = rosen_scratch;
+    RosenProblem prob{ws.n, ws.x};
     ws.cta = blockIdx.x;
     GroupBarrier gb{bar, 0u, ws.G};
     int status = 0;

@@ -517,7 +517,7 @@ constexpr size_t kSolveScratchBytes = (size_t)kNumDots * (kThreads / 2) * sizeof
 
 // Problem concept:
 //   double eval_partial(const double *x)        phase E, all threads; returns the CTA's partial f
-//   double grad_coord(int k, const double *x, double &faug)   reduced gradient of coordinate k
+//   double grad_coord(int k, double xk, double &faug)   reduced gradient of coordinate k (xk = x[k])
 // Runs to completion; returns the number of evaluations (identical in all CTAs). status: 0 ok,
 // 1 line search failed (ExceptionWithIflag in the reference), 2 numeric trouble.
 template <class Problem>
@@ -562,31 +562,56 @@ __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier 
         for (int i = 0; i < kNumDots; ++i)
             pd[i] = 0.0;
         double *ynew = ws.Y + (size_t)point * n;
-        for (int k = k0 + threadIdx.x; k < k1; k += kThreads) {
-            double faug = 0.0;
-            const double gk = prob.grad_coord(k, ws.x, faug);
-            const double xk = __ldcg(ws.x + k);
-            ws.g[k] = gk;
-            pd[D_F] += faug;
-            pd[D_GG] += gk * gk;
-            pd[D_XX] += xk * xk;
-            if (!first) {
-                const double dk = ws.d[k];
-                const double yn = gk - ws.gold[k];
-                ynew[k] = yn;
-                pd[D_GD] += gk * dk;
-                pd[D_GYN] += gk * yn;
-                pd[D_YNYN] += yn * yn;
-                pd[D_DYN] += dk * yn;
+        // two coordinates per trip (k, k + kThreads): every load of both is issued before any use
+        for (int kb = k0 + threadIdx.x; kb < k1; kb += 2 * kThreads) {
+            int kk[2] = {kb, kb + kThreads};
+            const bool ok[2] = {true, kb + kThreads < k1};
+            if (!ok[1])
+                kk[1] = kb;
+            double xk[2], dk[2], go[2], si[2][kLbfgsM], yi[2][kLbfgsM];
 #pragma unroll
-                for (int i = 0; i < kLbfgsM; ++i) {
-                    if ((valid >> i) & 1u) {
-                        const double si = ws.S[(size_t)i * n + k], yi = ws.Y[(size_t)i * n + k];
-                        pd[D_GS + i] += gk * si;
-                        pd[D_GY + i] += gk * yi;
-                        pd[D_YNS + i] += yn * si;
-                        pd[D_YNY + i] += yn * yi;
-                        pd[D_DY + i] += dk * yi;
+            for (int u = 0; u < 2; ++u) {
+                xk[u] = __ldcg(ws.x + kk[u]);
+                dk[u] = go[u] = 0.0;
+                if (!first) {
+                    dk[u] = ws.d[kk[u]];
+                    go[u] = ws.gold[kk[u]];
+#pragma unroll
+                    for (int i = 0; i < kLbfgsM; ++i) {
+                        si[u][i] = yi[u][i] = 0.0;
+                        if ((valid >> i) & 1u) {
+                            si[u][i] = ws.S[(size_t)i * n + kk[u]];
+                            yi[u][i] = ws.Y[(size_t)i * n + kk[u]];
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (!ok[u])
+                    continue;
+                double faug = 0.0;
+                const double gk = prob.grad_coord(kk[u], xk[u], faug);
+                ws.g[kk[u]] = gk;
+                pd[D_F] += faug;
+                pd[D_GG] += gk * gk;
+                pd[D_XX] += xk[u] * xk[u];
+                if (!first) {
+                    const double yn = gk - go[u];
+                    ynew[kk[u]] = yn;
+                    pd[D_GD] += gk * dk[u];
+                    pd[D_GYN] += gk * yn;
+                    pd[D_YNYN] += yn * yn;
+                    pd[D_DYN] += dk[u] * yn;
+#pragma unroll
+                    for (int i = 0; i < kLbfgsM; ++i) {
+                        if ((valid >> i) & 1u) {
+                            pd[D_GS + i] += gk * si[u][i];
+                            pd[D_GY + i] += gk * yi[u][i];
+                            pd[D_YNS + i] += yn * si[u][i];
+                            pd[D_YNY + i] += yn * yi[u][i];
+                            pd[D_DY + i] += dk[u] * yi[u][i];
+                        }
                     }
                 }
             }

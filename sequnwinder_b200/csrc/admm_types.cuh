@@ -15,7 +15,7 @@
 namespace sqw {
 
 constexpr int kLbfgsM = 5;        // L-BFGS history length (LOne.java:868)
-constexpr int kThreads = 256;     // threads per CTA of the x-update kernel
+constexpr int kThreads = 384;     // threads per CTA of the x-update kernel (12 warps, 3 per SMSP)
 constexpr int kWarps = kThreads / 32;
 constexpr int kNumDots = 32;      // scalar partials exchanged per evaluation (see admm_solver.cuh)
 constexpr int kMaxEdgesPerLeaf = 32;
@@ -105,7 +105,7 @@ struct AdmmDev {
     double *spart; // [T_local][G][kNumDots] per-CTA partial scalars
     unsigned *bar; // [T_local][32] group barrier counters (one per 128-byte line)
     int *nfev;     // [T_local] evaluations done by the last x-update
-    long long *prof; // optional [T_local*G][8] phase cycle counters (SQW_ADMM_PROFILE=1)
+    long long *prof; // optional [T_local*G][16] phase cycle counters (SQW_ADMM_PROFILE=1)
 
     // ---- consensus exchange buffers ----
     double *sum1;  // [npad + upad]  sum over blocks of x_t | u_t   (allreduced when world > 1)

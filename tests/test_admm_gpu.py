@@ -108,8 +108,8 @@ def test_trainer_matches_oracle_fixed_iterations(oracle, cfg, n, mf, T, A, S):
 
 def test_rho_adaptation_and_convergence_paths(oracle):
     """A run long enough to double rho, converge an ADMM run early and finish the outer loop."""
-    p = make_problem("cfg1", 400, max_features=12)
-    T, A, S = 4, 400, 15
+    p = make_problem("cfg1", 400, max_features=200)
+    T, A, S = 2, 400, 15
     xo, smo, tr = oracle.lone_execute(p.x0, p.smx0, p.data, p.cls, p.weights, p.st, p.num_classes,
                                       num_threads=T, admm_max_itr=A, nodes_max_itr=S)
     lo = run_gpu(p, T, A, S)
