@@ -335,6 +335,12 @@ def main():
 
     peak, peak_src = measured_peak_hbm()
     achieved = eval_bytes / eval_s / 1e9 if eval_s > 0 else 0.0
+    # DRAM traffic per x-update launch: ncu --set full capture of round 1 (profiles/
+    # r01_ncu_prof_xupdate_r1c.txt): 3.66 GB read + 0.46 GB written for the 35 evaluation rounds of
+    # the captured launch = 117.6 MB per evaluation round of 8 blocks (one pass over the 104 MB
+    # matrix + partial gradients), scaled to this run's average evaluation rounds per launch.
+    xupdate_launches = max(1, iters)
+    traffic = 117.6e6 * (evals / BLOCKS_PER_GPU / world) / xupdate_launches if world == 1 else None
     kmer_bytes = n_sites * (LENGTH + 4 * kc.numK) * args.steps
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -358,7 +364,8 @@ def main():
         "kmer_roofline": {"bound": "hbm", "achieved": kmer_bytes / kmer_s / 1e9, "peak": peak,
                           "unit": "GB/s", "frac": kmer_bytes / kmer_s / 1e9 / peak},
         "roofline": {"bound": "hbm", "kernel": "admm_xupdate_kernel", "achieved": achieved,
-                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "algorithmic_bytes_per_launch": eval_bytes / max(1, iters),
                      "peak_source": peak_src,
                      "note": "algorithmic bytes = evaluations x (2 n_b dim 8 + 2 n_b C 8 + 12 n_b "
                              "+ 2 C dim 8) over the summed durations of the x-update kernels, which "
