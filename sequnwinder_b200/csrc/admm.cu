@@ -388,8 +388,7 @@ void sqw_admm_destroy(sqw_admm *h)
     cudaSetDevice(h->device);
     if (h->stream)
         cudaStreamSynchronize(h->stream);
-    if (h->comm && nccl_api() && nccl_api()->CommDestroy)
-        nccl_api()->CommDestroy(h->comm);
+    // the NCCL communicator is shared between handles and outlives them (see sqw_admm_set_comm)
     for (void *p : h->allocs)
         cudaFree(p);
     if (h->h_ring) {
@@ -540,6 +539,22 @@ int sqw_admm_set_comm(sqw_admm *h, int32_t rank, int32_t world, const uint8_t nc
     NcclApi *api = nccl_api();
     if (!api)
         return set_error(SQW_ERR_NCCL, "libnccl.so.2 could not be loaded");
+    // One communicator per ncclUniqueId per process: an id can initialise only one communicator,
+    // and every LOne instance of a run (1 + x CV folds) shares it. It lives until process exit.
+    struct Cached {
+        std::string id;
+        int rank, world;
+        void *comm;
+    };
+    static std::vector<Cached> cache;
+    const std::string key(reinterpret_cast<const char *>(nccl_id), 128);
+    for (const Cached &c : cache)
+        if (c.id == key) {
+            if (c.rank != rank || c.world != world)
+                return set_error(SQW_ERR_INVALID_ARG, "ncclUniqueId reused with a different rank/world");
+            h->comm = c.comm;
+            return SQW_OK;
+        }
     NcclUid id;
     memcpy(id.internal, nccl_id, 128);
     SQW_CUDA_CHECK(cudaSetDevice(h->device));
@@ -547,6 +562,7 @@ int sqw_admm_set_comm(sqw_admm *h, int32_t rank, int32_t world, const uint8_t nc
     if (rc != 0)
         return set_error(SQW_ERR_NCCL, "ncclCommInitRank failed: %s",
                          api->GetErrorString ? api->GetErrorString(rc) : "?");
+    cache.push_back(Cached{key, rank, world, h->comm});
     return SQW_OK;
 }
 

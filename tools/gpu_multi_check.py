@@ -1,0 +1,33 @@
+"""torchrun --nproc-per-node 2 tools/gpu_multi_check.py : T fixed, blocks spread over ranks;
+results must equal the oracle's single-process run (and hence the 1-GPU run) up to rounding."""
+import os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
+from oracle import pyoracle as O
+from sequnwinder_b200 import optimizer as opt, parallel
+from helpers import make_problem
+
+info = parallel.rank_info_from_env()
+torch.cuda.set_device(info.local_rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", info.local_rank))
+nid = parallel.share_nccl_id()
+for (cfg, n, mf, T, A, S) in [("cfg1", 500, 60, 4, 30, 2), ("cfg2", 4000, None, 8, 4, 1), ("cfg1", 400, 200, 2, 400, 15)]:
+    p = make_problem(cfg, n, max_features=mf)
+    lo = opt.LOneCuda(p.x0.copy(), p.smx0.copy(), p.data)
+    lo.setRidge(10.0); lo.setADMMmaxItrs(A); lo.setSeqUnwinderMaxIts(S)
+    lo.setClassStructure(p.crs); lo.setClsMembership(p.cls); lo.setInstanceWeights(p.weights)
+    lo.setNumClasses(p.num_classes); lo.setNumPredictors(p.data.shape[1] - 1); lo.setPho(1.7); lo.set_numThreads(T)
+    lo.setComm(info.rank, info.world, nid)
+    lo.execute()
+    x = torch.from_numpy(lo.getX().copy()).cuda()
+    xs = [torch.empty_like(x) for _ in range(info.world)]
+    dist.all_gather(xs, x)
+    same = all(torch.equal(xs[0], t) for t in xs)      # replicated consensus state must be bitwise equal
+    if info.rank == 0:
+        xo, smo, tr = O.lone_execute(p.x0, p.smx0, p.data, p.cls, p.weights, p.st, p.num_classes, num_threads=T, admm_max_itr=A, nodes_max_itr=S, host_threads=8)
+        err = np.abs(lo.getX() - xo).max() / np.abs(xo).max()
+        print(f"{cfg} n={n} T={T} world={info.world}: ranks bitwise equal {same}; admm iters {lo.log.admm_iters} vs oracle {tr.admm_iters}; x rel err {err:.3e}; local blocks {lo.log.nfev.shape[1]}", flush=True)
+        assert same and lo.log.admm_iters == tr.admm_iters and err < 1e-6
+dist.barrier()
+dist.destroy_process_group()
