@@ -156,3 +156,21 @@ def test_errors_are_reported():
     lo.set_numThreads(1000)              # more blocks than rows
     with pytest.raises(RuntimeError):
         lo.execute()
+
+
+def test_two_gpu_sharding_matches_oracle():
+    """T fixed, blocks spread over 2 ranks (ncclAllReduce consensus): same iteration counts and
+    weights as the oracle, bitwise-identical replicated state on both ranks. Needs 2 GPUs."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (covered on CPU by tests/test_parallel_gloo.py)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                        "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port",
+                        "29533", os.path.join(root, "tools", "gpu_multi_check.py")],
+                       cwd=root, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ranks bitwise equal True") == 3
