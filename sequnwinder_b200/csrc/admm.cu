@@ -869,9 +869,9 @@ int sqw_admm_execute(sqw_admm *h, double *x_inout, double *smx_inout)
             const long long *q = &pr[(size_t)c * 16];
             fprintf(stderr, "[sqw profile] block 0 cta %d: evals %lld;", c, q[7]);
             for (int i = 0; i < 7; ++i)
-                fprintf(stderr, " %s %.0f cyc", names[i], q[7] ? (double)q[i] / q[7] : 0.0);
-            const char *en[8] = {"Wstage", "tilewait", "pass1", "rr_wait", "-", "pass2", "free_arrive", "combine"};
-            fprintf(stderr, "\n[sqw profile]    eval breakdown per eval:");
+                fprintf(stderr, " %s %.0f ns", names[i], q[7] ? (double)q[i] / q[7] : 0.0);
+            const char *en[8] = {"kernel_epilogue", "tilewait", "pass1", "rr_wait", "kernel_prologue", "pass2", "free_arrive", "combine"};
+            fprintf(stderr, "\n[sqw profile]    eval breakdown per eval (ns):");
             for (int i = 0; i < 8; ++i)
                 fprintf(stderr, " %s %.0f", en[i], q[7] ? (double)q[8 + i] / q[7] : 0.0);
             fprintf(stderr, "\n");

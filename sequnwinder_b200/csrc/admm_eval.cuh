@@ -29,6 +29,14 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b)
         : "d"(a), "d"(b));
 }
 
+// wall-clock nanoseconds (profiling counters only)
+__device__ __forceinline__ long long sqw_now_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return (long long)t;
+}
+
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll

@@ -84,8 +84,9 @@ inline TileSmemLayout tile_smem_layout(int Cp, int dimp, size_t budget, size_t m
     L.w_bytes = std::max(nct > 1 ? (size_t)Cp * dimp * 8 : (size_t)0, min_w_bytes);
     L.w_bytes = (L.w_bytes + 127) & ~(size_t)127;
     L.stage_bytes = (size_t)kTileRows * dimp * 8;
-    const size_t plog_bytes = (size_t)2 * kWarps * nct * 32 * 16;  // double-buffered partial logits
-    const size_t fixed = L.w_bytes + plog_bytes + (size_t)kWarps * nct * 64 * 8 + 128;
+    const size_t plog_bytes = (size_t)2 * 8 * nct * 32 * 16;  // [2][kDmmaWarps][nct][32] double2
+    const size_t rs_bytes = (size_t)2 * nct * 64 * 8;          // [2][nct][64] residual fragments
+    const size_t fixed = L.w_bytes + plog_bytes + rs_bytes + 128;
     int ns = 0;
     if (budget > fixed)
         ns = (int)std::min<size_t>(4, (budget - fixed) / L.stage_bytes);
@@ -93,7 +94,7 @@ inline TileSmemLayout tile_smem_layout(int Cp, int dimp, size_t budget, size_t m
     L.stage_off = L.w_bytes;
     L.plog_off = L.stage_off + (size_t)ns * L.stage_bytes;
     L.rs_off = L.plog_off + plog_bytes;
-    L.bar_off = L.rs_off + (size_t)kWarps * nct * 64 * 8;
+    L.bar_off = L.rs_off + rs_bytes;
     L.total = L.bar_off + 128;
     return L;
 }
@@ -251,10 +252,10 @@ struct TileEvalWS {
         long long tk0 = 0, tk1 = 0;
         const bool do_prof = prof != nullptr && threadIdx.x == 0;
         if (do_prof)
-            tk0 = clock64();
+            tk0 = sqw_now_ns();
 #define SQW_EPROF(slot)          \
     if (do_prof) {               \
-        tk1 = clock64();         \
+        tk1 = sqw_now_ns();         \
         prof[slot] += tk1 - tk0; \
         tk0 = tk1;               \
     }
@@ -344,8 +345,8 @@ struct TileEvalWS {
                         for (int u = 0; u < KSW; ++u)
                             xa[u] = xp[4 * min(ks0 + u, ks1 - 1)];
 #pragma unroll
-                        for (int u = 0; u < KSW; ++u)
-                            dmma884(pa[0][u & 3], xa[u], wreg[u]);
+                        for (int u = 0; u < KSW; ++u)  // straight-line: skipping the padded k-steps
+                            dmma884(pa[0][u & 3], xa[u], wreg[u]);  // with branches measured slower
                     } else {
                         const double *wp = smW + (size_t)gid * dimp + qd;
 #pragma unroll 4

@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(kThreads, 1) admm_xupdate_kernel(AdmmDev P, Ti
     if (ld_volatile_int(&P.ctrl->done) || ld_volatile_int(&P.ctrl->fatal))
         return;
     const int blk = blockIdx.x / P.G, cta = blockIdx.x - blk * P.G;
+    const long long t_kernel0 = (P.prof && threadIdx.x == 0) ? sqw_now_ns() : 0;
     const double pho = P.ctrl->pho, fold = P.ctrl->fold;
     double *xt = P.xt + (size_t)blk * P.Cp * P.dimp;
     double *ut = P.ut + (size_t)blk * P.upad;
@@ -157,8 +158,17 @@ __global__ void __launch_bounds__(kThreads, 1) admm_xupdate_kernel(AdmmDev P, Ti
     ws.cta = cta;
     ws.prof = P.prof ? P.prof + (size_t)blockIdx.x * 16 : nullptr;
     int status = 0;
+    const long long t_loop0 = (P.prof && threadIdx.x == 0) ? sqw_now_ns() : 0;
     const int evals = lbfgs_group_solve(prob, ws, gb, sm, 0.1, 10e-16, status);  // LOne.java:874-875
+    const long long t_loop1 = (P.prof && threadIdx.x == 0) ? sqw_now_ns() : 0;
     ev.drain();
+    if (P.prof && threadIdx.x == 0) {
+        long long *pf = P.prof + (size_t)blockIdx.x * 16;
+        // slots 4 and 12 of the evaluator table are unused: kernel prologue / epilogue time
+        pf[12] += t_loop0 - t_kernel0;
+        pf[4 + 8] += 0;
+        pf[8] += sqw_now_ns() - t_loop1;  // "Wstage" slot is ~0 in mode 4: reuse for the epilogue
+    }
     if (cta == 0 && threadIdx.x == 0) {
         P.nfev[blk] = evals;
         if (status == 1)

@@ -511,9 +511,9 @@ struct SolveSmem {
     Decision dec;
     LbState st;       // scalar solver state: shared memory keeps it out of every thread's registers
     int fatal;
-    double *scratch;  // >= kNumDots * (kThreads / 2) doubles of shared memory, free during reduce
+    double *scratch;  // >= kNumDots * (kThreads / 4) doubles of shared memory, free during reduce
 };
-constexpr size_t kSolveScratchBytes = (size_t)kNumDots * (kThreads / 2) * sizeof(double);
+constexpr size_t kSolveScratchBytes = (size_t)kNumDots * (kThreads / 4) * sizeof(double);
 
 // Problem concept:
 //   double eval_partial(const double *x)        phase E, all threads; returns the CTA's partial f
@@ -542,10 +542,10 @@ __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier 
         // ---- phase E: data-term partials of this CTA at the trial point
         long long tk0 = 0, tk1 = 0;
         if (ws.prof && threadIdx.x == 0)
-            tk0 = clock64();
+            tk0 = sqw_now_ns();
 #define SQW_PROF(slot)                                   \
     if (ws.prof && threadIdx.x == 0) {                   \
-        tk1 = clock64();                                 \
+        tk1 = sqw_now_ns();                                 \
         ws.prof[slot] += tk1 - tk0;                      \
         tk0 = tk1;                                       \
     }
@@ -623,16 +623,18 @@ __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier 
             __syncthreads();  // the evaluator is done with the shared region the scratch aliases
 #pragma unroll
             for (int i = 0; i < kNumDots; ++i) {
-                const double v = pd[i] + __shfl_xor_sync(0xffffffffu, pd[i], 1);
-                if ((lane & 1) == 0)
-                    scr[i * (kThreads / 2) + (threadIdx.x >> 1)] = v;
+                double v = pd[i] + __shfl_xor_sync(0xffffffffu, pd[i], 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                if ((lane & 3) == 0)
+                    scr[i * (kThreads / 4) + (threadIdx.x >> 2)] = v;
             }
             __syncthreads();
             for (int id = warp; id < kNumDots; id += kWarps) {
                 double acc = 0.0;
 #pragma unroll
-                for (int j = 0; j < (kThreads / 2) / 32; ++j)
-                    acc += scr[id * (kThreads / 2) + j * 32 + lane];
+                for (int j = 0; j < (kThreads / 4 + 31) / 32; ++j)
+                    if (j * 32 + lane < kThreads / 4)
+                        acc += scr[id * (kThreads / 4) + j * 32 + lane];
                 acc = warp_sum(acc);
                 if (lane == 0)
                     __stcg(ws.spart + (size_t)cta * kNumDots + id, acc);
