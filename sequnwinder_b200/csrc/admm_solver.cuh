@@ -562,56 +562,44 @@ __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier 
         for (int i = 0; i < kNumDots; ++i)
             pd[i] = 0.0;
         double *ynew = ws.Y + (size_t)point * n;
-        // two coordinates per trip (k, k + kThreads): every load of both is issued before any use
-        for (int kb = k0 + threadIdx.x; kb < k1; kb += 2 * kThreads) {
-            int kk[2] = {kb, kb + kThreads};
-            const bool ok[2] = {true, kb + kThreads < k1};
-            if (!ok[1])
-                kk[1] = kb;
-            double xk[2], dk[2], go[2], si[2][kLbfgsM], yi[2][kLbfgsM];
+        // one coordinate per trip (a slice is rarely longer than the CTA): every load of the
+        // coordinate is issued before any use
+        for (int k = k0 + threadIdx.x; k < k1; k += kThreads) {
+            const double xk = __ldcg(ws.x + k);
+            double dk = 0.0, go = 0.0, si[kLbfgsM], yi[kLbfgsM];
+            if (!first) {
+                dk = ws.d[k];
+                go = ws.gold[k];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                xk[u] = __ldcg(ws.x + kk[u]);
-                dk[u] = go[u] = 0.0;
-                if (!first) {
-                    dk[u] = ws.d[kk[u]];
-                    go[u] = ws.gold[kk[u]];
-#pragma unroll
-                    for (int i = 0; i < kLbfgsM; ++i) {
-                        si[u][i] = yi[u][i] = 0.0;
-                        if ((valid >> i) & 1u) {
-                            si[u][i] = ws.S[(size_t)i * n + kk[u]];
-                            yi[u][i] = ws.Y[(size_t)i * n + kk[u]];
-                        }
+                for (int i = 0; i < kLbfgsM; ++i) {
+                    si[i] = yi[i] = 0.0;
+                    if ((valid >> i) & 1u) {
+                        si[i] = ws.S[(size_t)i * n + k];
+                        yi[i] = ws.Y[(size_t)i * n + k];
                     }
                 }
             }
+            double faug = 0.0;
+            const double gk = prob.grad_coord(k, xk, faug);
+            ws.g[k] = gk;
+            pd[D_F] += faug;
+            pd[D_GG] += gk * gk;
+            pd[D_XX] += xk * xk;
+            if (!first) {
+                const double yn = gk - go;
+                ynew[k] = yn;
+                pd[D_GD] += gk * dk;
+                pd[D_GYN] += gk * yn;
+                pd[D_YNYN] += yn * yn;
+                pd[D_DYN] += dk * yn;
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                if (!ok[u])
-                    continue;
-                double faug = 0.0;
-                const double gk = prob.grad_coord(kk[u], xk[u], faug);
-                ws.g[kk[u]] = gk;
-                pd[D_F] += faug;
-                pd[D_GG] += gk * gk;
-                pd[D_XX] += xk[u] * xk[u];
-                if (!first) {
-                    const double yn = gk - go[u];
-                    ynew[kk[u]] = yn;
-                    pd[D_GD] += gk * dk[u];
-                    pd[D_GYN] += gk * yn;
-                    pd[D_YNYN] += yn * yn;
-                    pd[D_DYN] += dk[u] * yn;
-#pragma unroll
-                    for (int i = 0; i < kLbfgsM; ++i) {
-                        if ((valid >> i) & 1u) {
-                            pd[D_GS + i] += gk * si[u][i];
-                            pd[D_GY + i] += gk * yi[u][i];
-                            pd[D_YNS + i] += yn * si[u][i];
-                            pd[D_YNY + i] += yn * yi[u][i];
-                            pd[D_DY + i] += dk[u] * yi[u][i];
-                        }
+                for (int i = 0; i < kLbfgsM; ++i) {
+                    if ((valid >> i) & 1u) {
+                        pd[D_GS + i] += gk * si[i];
+                        pd[D_GY + i] += gk * yi[i];
+                        pd[D_YNS + i] += yn * si[i];
+                        pd[D_YNY + i] += yn * yi[i];
+                        pd[D_DY + i] += dk * yi[i];
                     }
                 }
             }

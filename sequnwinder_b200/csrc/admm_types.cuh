@@ -15,7 +15,8 @@
 namespace sqw {
 
 constexpr int kLbfgsM = 5;        // L-BFGS history length (LOne.java:868)
-constexpr int kThreads = 384;     // threads per CTA of the x-update kernel (12 warps, 3 per SMSP)
+constexpr int kThreads = 352;     // threads per CTA of the x-update kernel: 8 DMMA + 2 softmax +
+                                  // 1 producer warp; 65536 / 352 leaves 184 registers per thread
 constexpr int kWarps = kThreads / 32;
 constexpr int kNumDots = 32;      // scalar partials exchanged per evaluation (see admm_solver.cuh)
 constexpr int kMaxEdgesPerLeaf = 32;
