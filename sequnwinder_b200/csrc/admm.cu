@@ -151,6 +151,7 @@ static XKernel xupdate_kernel(int nct, int mode)
 {
     switch (nct * 8 + mode) {
     case 8 + 4: return admm_xupdate_kernel<1, 4>;
+    case 8 + 5: return admm_xupdate_kernel<1, 5>;
     case 8 + 1: return admm_xupdate_kernel<1, 1>;
     case 8 + 2: return admm_xupdate_kernel<1, 2>;
     case 16 + 4: return admm_xupdate_kernel<2, 4>;
@@ -167,6 +168,7 @@ static EKernel eval_kernel(int nct, int mode)
 {
     switch (nct * 8 + mode) {
     case 8 + 4: return admm_eval_kernel<1, 4>;
+    case 8 + 5: return admm_eval_kernel<1, 5>;
     case 8 + 1: return admm_eval_kernel<1, 1>;
     case 8 + 2: return admm_eval_kernel<1, 2>;
     case 16 + 4: return admm_eval_kernel<2, 4>;
@@ -221,7 +223,7 @@ static int prepare(sqw_admm *h)
     const int n_sm = prop.multiProcessorCount;
     const int mode = h->eval_mode;
     const size_t w_bytes = (size_t)D.Cp * D.wstride * sizeof(double);
-    if (mode == 4)
+    if (mode == 4 || mode == 5)
         h->xupdate_smem = h->layout.total;
     else if (mode == 1)
         h->xupdate_smem = std::max(w_bytes, kSolveScratchBytes);
@@ -616,6 +618,8 @@ static int plan_blocks(sqw_admm *h, int64_t n_rows, int32_t dim, int32_t num_cla
     const bool ws_ok = L.NS >= 3 && L.NS <= 4 && (dimp4 + 15) / 16 <= kDmmaWarps * 6 &&
                        dimp4 / 4 <= kDmmaWarps * 24;
     int mode = ws_ok ? 4 : ((size_t)Cp * dimp8 * 8 <= 160 * 1024 ? 1 : 2);
+    if (mode == 4 && nct == 1 && (dimp4 / 4 + kDmmaWarps - 1) / kDmmaWarps <= 21)
+        mode = 5;  // same kernel with 21 instead of 24 unrolled k-steps per DMMA warp
     if (const char *env = getenv("SQW_ADMM_EVAL_MODE")) {  // test hook: force a more general path
         const int m = atoi(env);
         if (m == 1 && (size_t)Cp * dimp8 * 8 <= 160 * 1024)
@@ -625,7 +629,7 @@ static int plan_blocks(sqw_admm *h, int64_t n_rows, int32_t dim, int32_t num_cla
     }
     h->eval_mode = mode;
     h->layout = L;
-    D.dimp = (mode == 4) ? dimp4 : dimp8;
+    D.dimp = (mode == 4 || mode == 5) ? dimp4 : dimp8;
     return SQW_OK;
 }
 

@@ -135,7 +135,7 @@ struct WsSmemLayout {
     static constexpr int kBarPl = 1, kBarRr = 3, kBarFree = 5;  // kBarFree + stage (<= 4 stages)
 };
 
-template <int NCT>
+template <int NCT, int KSW_ = 24>
 struct TileEvalWS {
     static constexpr int NBG = 6;  // 16-column groups per DMMA warp: rows up to 8*6*16 = 768 columns
     const AdmmDev &P;
@@ -260,7 +260,7 @@ struct TileEvalWS {
         tk0 = tk1;               \
     }
         constexpr bool W_REG = (NCT == 1);  // one class tile: this warp's W fragments live in registers
-        constexpr int KSW = 24;             // k-steps (4 columns) per DMMA warp: dimp <= 8*24*4 = 768
+        constexpr int KSW = KSW_;           // k-steps (4 columns) per DMMA warp: dimp <= 8*KSW*4
         if (!W_REG) {
             for (int i = threadIdx.x; i < Cp * dimp; i += kThreads)
                 smW[i] = (i < P.npad) ? __ldcg(xcur + i) : 0.0;
@@ -317,6 +317,9 @@ struct TileEvalWS {
                 }
 #pragma unroll
                 for (int i = 0; i < NBG; ++i) {
+                    // only a warp's last group can lie beyond the row: one warp-uniform branch
+                    if (i == NBG - 1 && warp + kDmmaWarps * i >= ngroups)
+                        break;
 #pragma unroll
                     for (int ct = 0; ct < NCT; ++ct) {
                         dmma884(acc[i][0][ct], a[ct][0], x0[i].x);

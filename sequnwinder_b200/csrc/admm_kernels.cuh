@@ -60,7 +60,11 @@ struct EvalSelect {
 };
 template <int NCT>
 struct EvalSelect<NCT, 4> {
-    typedef TileEvalWS<NCT> type;
+    typedef TileEvalWS<NCT, 24> type;
+};
+template <int NCT>
+struct EvalSelect<NCT, 5> {   // MODE 4 with 21 k-steps per DMMA warp (rows <= 672 columns)
+    typedef TileEvalWS<NCT, 21> type;
 };
 
 template <class Eval>
@@ -466,7 +470,7 @@ admm_eval_kernel(AdmmDev P, TileSmemLayout L, double pho, double *f_out)
     ev.init(smem_raw, L, sm.red);
     BlockProblem<Eval> prob{P, blk, cta, pho, P.ut + (size_t)blk * P.upad, ev};
     double fpart = prob.eval_partial(xt);
-    if (MODE == 4) {
+    if (MODE == 4 || MODE == 5) {
         // further evaluations exercise the ring wrap-around / resident path; results must agree
         for (int rep = 0; rep < 2; ++rep) {
             __syncthreads();
