@@ -72,7 +72,9 @@ int sqw_kmer_count_dev(const uint8_t *d_bases, const int64_t *d_offsets, int64_t
  * Replaces framework/LOne.java (an framework/Optimizer.java:5-27 plug-in) together with its
  * inner solver framework/LBFGS.java + Mcsrch.java. Call order mirrors
  * framework/Classifier.java:422-449:
- *   create -> set_problem -> set_structure -> set_params -> [set_comm] -> execute -> destroy
+ *   create -> set_structure -> set_params -> [set_comm] -> set_problem -> execute -> destroy
+ * (set_problem comes last because the row blocking depends on T; the Java shim keeps the
+ * caller's order by uploading inside execute())
  * ---------------------------------------------------------------------------------------- */
 typedef struct sqw_admm sqw_admm;
 
@@ -146,6 +148,35 @@ int sqw_admm_get_stats(const sqw_admm *h, sqw_admm_stats *out);
 int sqw_admm_get_log(const sqw_admm *h, int32_t cap, int32_t *rows_out, int32_t *outer,
                      int32_t *itr, double *pho, double *fold, double *primal, double *dual,
                      int32_t *nfev, int32_t *admm_iters_per_outer);
+
+/* ------------------------------------------------------------------------------------------
+ * The steps either side of the trainer, device resident. All pointers are
+ * device pointers; `stream` is a cudaStream_t.
+ * ---------------------------------------------------------------------------------------- */
+
+/* f-1a. Column statistics of the dense count matrix (n x numK int32): which columns survive
+ * weka RemoveUseless (non-constant over the rows; framework/Classifier.java:305-308), and the
+ * instance-weighted mean / SD of every column (Classifier.java:337-372; total_weight = sum of w).
+ * d_keep_idx receives the num_kept surviving column indices in ascending order (capacity numK);
+ * d_mean / d_sd are indexed by ORIGINAL column (numK each). Synchronises the stream once. */
+int sqw_prepare_plan_dev(const int32_t *d_counts, int64_t n, int64_t numK, const double *d_w,
+                         double total_weight, int32_t *d_keep_idx, int32_t *num_kept_out,
+                         double *d_mean, double *d_sd, void *stream);
+
+/* f-1b. The standardised training matrix the trainer takes: d_X is n x (num_kept+1) fp64
+ * row-major, column 0 == 1 (Classifier.java:344,374-381). Replaces the tmpCounts.mat -> CSVLoader
+ * -> ARFF text round trip of loaddata/MakeArff.java:255-288. Asynchronous. */
+int sqw_prepare_apply_dev(const int32_t *d_counts, int64_t n, int64_t numK, const int32_t *d_keep_idx,
+                          int32_t num_kept, const double *d_mean, const double *d_sd, double *d_X,
+                          void *stream);
+
+/* f-2. Batched Classifier.evaluateProbability (Classifier.java:244-287) on raw count rows:
+ * d_par is m_Par, dim x num_classes row-major (de-standardised weights, dim = num_kept+1);
+ * d_prob (n x num_classes, may be NULL) and d_argmax (n, first maximum, may be NULL) are
+ * outputs. Asynchronous. */
+int sqw_predict_dev(const double *d_par, int32_t dim, int32_t num_classes, const int32_t *d_counts,
+                    int64_t n, int64_t numK, const int32_t *d_keep_idx, double *d_prob,
+                    int32_t *d_argmax, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Building blocks exposed for parity tests and micro-benchmarks (same kernels execute() uses).

@@ -53,6 +53,12 @@ SYMBOLS = {
     "sqw_admm_get_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sqw_admm_get_log": (C.c_int, [C.c_void_p, C.c_int32, i32p, i32p, i32p, f64p, f64p, f64p,
                                    f64p, i32p, i32p]),
+    "sqw_prepare_plan_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_double,
+                                       C.c_void_p, i32p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sqw_prepare_apply_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int32,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sqw_predict_dev": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int64,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sqw_admm_eval": (C.c_int, [C.c_void_p, f64p, f64p, C.c_double, f64p, f64p]),
     "sqw_lbfgs_rosenbrock": (C.c_int, [C.c_int32, f64p, C.c_double, i32p, i32p, i32p]),
 }

@@ -161,3 +161,67 @@ class Classifier:
             v[self.prep.keep] = self.sm_Par[1:, idx]
             out[name] = v
         return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Device-resident versions of the steps either side of the trainer: torch
+# tensors are only device memory here; the arithmetic is in csrc/prepare_predict.cu.
+# ---------------------------------------------------------------------------------------------
+class DevicePrepared:
+    """Result of ``prepare_device``: cuda tensors X [n, F+1] fp64, keep_idx [F] int32,
+    mean / sd [numK] fp64 (indexed by original column)."""
+
+    def __init__(self, X, keep_idx, mean, sd):
+        self.X, self.keep_idx, self.mean, self.sd = X, keep_idx, mean, sd
+
+    @property
+    def num_kept(self) -> int:
+        return int(self.keep_idx.numel())
+
+
+def prepare_device(counts, weights) -> DevicePrepared:
+    """counts: cuda int32 [n, numK]; weights: cuda fp64 [n]. Classifier.java:300-381 on the GPU."""
+    import ctypes as C
+    import torch
+    from . import _lib
+
+    lib = _lib.load()
+    n, numK = counts.shape
+    dev = counts.device
+    keep = torch.empty(numK, dtype=torch.int32, device=dev)
+    mean = torch.empty(numK, dtype=torch.float64, device=dev)
+    sd = torch.empty(numK, dtype=torch.float64, device=dev)
+    nk = C.c_int32(0)
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    tot = float(weights.sum().item())
+    rc = lib.sqw_prepare_plan_dev(counts.data_ptr(), n, numK, weights.data_ptr(), tot, keep.data_ptr(),
+                                  C.byref(nk), mean.data_ptr(), sd.data_ptr(), stream)
+    if rc == _lib.SQW_ERR_INVALID_ARG and b"Sum of weights" in lib.sqw_last_error():
+        raise ValueError("Sum of weights of instances less than 1, please reweight!")
+    _lib.check(rc)
+    F = nk.value
+    keep = keep[:F].contiguous()
+    X = torch.empty((n, F + 1), dtype=torch.float64, device=dev)
+    _lib.check(lib.sqw_prepare_apply_dev(counts.data_ptr(), n, numK, keep.data_ptr(), F,
+                                         mean.data_ptr(), sd.data_ptr(), X.data_ptr(), stream))
+    return DevicePrepared(X, keep, mean, sd)
+
+
+def predict_device(par, counts, keep_idx, want_prob: bool = True):
+    """par: cuda fp64 [dim, C] (m_Par); counts: cuda int32 [n, numK]; keep_idx: cuda int32 [dim-1].
+    Returns (prob [n, C] or None, argmax [n] int32). Classifier.java:244-287 on the GPU."""
+    import ctypes as C
+    import torch
+    from . import _lib
+
+    lib = _lib.load()
+    dim, ncls = par.shape
+    n, numK = counts.shape
+    dev = counts.device
+    prob = torch.empty((n, ncls), dtype=torch.float64, device=dev) if want_prob else None
+    arg = torch.empty(n, dtype=torch.int32, device=dev)
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(lib.sqw_predict_dev(par.data_ptr(), dim, ncls, counts.data_ptr(), n, numK,
+                                   keep_idx.data_ptr(), prob.data_ptr() if want_prob else None,
+                                   arg.data_ptr(), stream))
+    return prob, arg
