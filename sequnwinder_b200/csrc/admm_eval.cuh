@@ -117,7 +117,7 @@ __device__ double eval_data_term(const AdmmDev &P, int blk, int cta, const doubl
 #pragma unroll
         for (int ct = 0; ct < NCT; ++ct)
             acc[ct][0] = acc[ct][1] = 0.0;
-#pragma unroll 4
+#pragma unroll 8
         for (int kk = 0; kk < nk; ++kk) {
             const double2 xa = __ldg(xp + 4 * kk);
 #pragma unroll
@@ -184,7 +184,7 @@ __device__ double eval_data_term(const AdmmDev &P, int blk, int cta, const doubl
 #pragma unroll
                 for (int ct = 0; ct < NCT; ++ct)
                     acc[i][h][ct][0] = acc[i][h][ct][1] = 0.0;
-#pragma unroll 2
+#pragma unroll 4
         for (int rq = 0; rq < nrq; ++rq) {
             const int row = r0 + 4 * rq + q;
             const bool rv = row < r1;

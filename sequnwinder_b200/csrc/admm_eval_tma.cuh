@@ -352,12 +352,24 @@ struct TileEvalWS {
                             dmma884(pa[0][u & 3], xa[u], wreg[u]);  // with branches measured slower
                     } else {
                         const double *wp = smW + (size_t)gid * dimp + qd;
-#pragma unroll 4
-                        for (int ks = ks0; ks < ks1; ++ks) {
-                            const double xa = xp[4 * ks];
+                        int ks = ks0;
+                        for (; ks + 3 < ks1; ks += 4) {
 #pragma unroll
-                            for (int ct = 0; ct < NCT; ++ct)
-                                dmma884(pa[ct][ks & 3], xa, wp[(size_t)ct * 8 * dimp + 4 * ks]);
+                            for (int u = 0; u < 4; ++u) {  // static chain index: registers
+                                const double xa = xp[4 * (ks + u)];
+#pragma unroll
+                                for (int ct = 0; ct < NCT; ++ct)
+                                    dmma884(pa[ct][u], xa, wp[(size_t)ct * 8 * dimp + 4 * (ks + u)]);
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 3; ++u) {
+                            if (ks + u < ks1) {
+                                const double xa = xp[4 * (ks + u)];
+#pragma unroll
+                                for (int ct = 0; ct < NCT; ++ct)
+                                    dmma884(pa[ct][u], xa, wp[(size_t)ct * 8 * dimp + 4 * (ks + u)]);
+                            }
                         }
                     }
                     double2 *dst = plog + ((size_t)(j & 1) * kDmmaWarps + warp) * NCT * 32;
@@ -503,6 +515,349 @@ struct TileEvalWS {
         SQW_EPROF(7)
 #undef SQW_EPROF
         return fs;
+    }
+};
+
+}  // namespace sqw
+
+// ----------------------------------------------------------------------------------------------
+// Column-chunked variant (MODE 6): rows of any length (k = 4..6, 4..7 feature sets, up to 24
+// classes). The row no longer fits shared memory, so the evaluation makes two TMA-staged passes
+// over the CTA's rows, KC columns at a time:
+//   pass 1  for every column chunk: partial logits of each 8-row tile (DMMA, K split over 8 warps)
+//           are summed by three helper warps (one per class tile) into a logits array in L2
+//           while the DMMA warps already work on the next tile (one __syncthreads per tile);
+//   softmax over the CTA's rows (one row per thread): logits -> residuals w_i (p - y), NLL;
+//   pass 2  for every column chunk: G[:, chunk] += R^T X[:, chunk], accumulators in registers for
+//           the chunk, one store per chunk.
+// X therefore crosses HBM twice per evaluation (the two-pass byte count of SURVEY.md 8d), always
+// through the TMA ring, never through per-thread global loads.
+namespace sqw {
+
+template <int NCT>
+struct ChunkCfg {
+    static constexpr int NBG = (NCT == 1) ? 6 : (NCT == 2 ? 4 : 3);  // column groups per DMMA warp
+    static constexpr int KC = 8 * NBG * 16 - 12;                      // 756 / 500 / 372 (= 4 mod 8)
+    static constexpr int KSW = (KC / 4 + 7) / 8;                      // k-steps per DMMA warp
+};
+
+inline TileSmemLayout chunk_smem_layout(int Cp, size_t budget, size_t min_w_bytes)
+{
+    TileSmemLayout L{};
+    const int nct = Cp / 8;
+    const int KC = nct == 1 ? ChunkCfg<1>::KC : (nct == 2 ? ChunkCfg<2>::KC : ChunkCfg<3>::KC);
+    L.w_off = 0;
+    L.w_bytes = std::max((size_t)Cp * KC * 8, min_w_bytes);
+    L.w_bytes = (L.w_bytes + 127) & ~(size_t)127;
+    L.stage_bytes = (size_t)kTileRows * KC * 8;
+    const size_t plog_bytes = (size_t)2 * 8 * nct * 32 * 16;
+    const size_t fixed = L.w_bytes + plog_bytes + 128;
+    int ns = 0;
+    if (budget > fixed)
+        ns = (int)std::min<size_t>(4, (budget - fixed) / L.stage_bytes);
+    L.NS = ns;
+    L.stage_off = L.w_bytes;
+    L.plog_off = L.stage_off + (size_t)ns * L.stage_bytes;
+    L.rs_off = L.plog_off + plog_bytes;
+    L.bar_off = L.rs_off;
+    L.total = L.bar_off + 128;
+    return L;
+}
+
+template <int NCT>
+struct TileEvalChunk {
+    static constexpr int NBG = ChunkCfg<NCT>::NBG, KC = ChunkCfg<NCT>::KC, KSW = ChunkCfg<NCT>::KSW;
+    const AdmmDev &P;
+    int blk, cta;
+    double *smW, *stages;
+    double2 *plog;
+    unsigned long long *full;
+    double *red;
+    int NS, r0, r1, ntiles, nch;
+    int cs, cph;            // consumer ring position
+    int p_pass, p_c, p_j;   // producer lane: next (pass, chunk, tile) to fetch
+    const double *Xb;
+
+    __device__ __forceinline__ int width(int c) const { return min(KC, P.dimp - c * KC); }
+
+    __device__ void issue(int c, int tile, int s)
+    {
+        const int row = r0 + tile * kTileRows;
+        const int rows = min(kTileRows, r1 - row);
+        const unsigned row_bytes = (unsigned)width(c) * 8u;
+        mbar_expect_tx(&full[s], (unsigned)rows * row_bytes);
+        double *dst = stages + (size_t)s * kTileRows * KC;
+        const double *src = Xb + (size_t)row * P.dimp + (size_t)c * KC;
+        for (int r = 0; r < rows; ++r)
+            bulk_g2s(dst + (size_t)r * KC, src + (size_t)r * P.dimp, row_bytes, &full[s]);
+    }
+    __device__ void refill(int s)
+    {
+        issue(p_c, p_j, s);
+        if (++p_j == ntiles) {
+            p_j = 0;
+            if (++p_c == nch) {
+                p_c = 0;
+                p_pass ^= 1;
+            }
+        }
+    }
+
+    __device__ void init(unsigned char *smem, const TileSmemLayout &L, double *red_)
+    {
+        smW = reinterpret_cast<double *>(smem + L.w_off);
+        stages = reinterpret_cast<double *>(smem + L.stage_off);
+        plog = reinterpret_cast<double2 *>(smem + L.plog_off);
+        full = reinterpret_cast<unsigned long long *>(smem + L.bar_off);
+        red = red_;
+        NS = L.NS;
+        cta_row_range(P, cta, r0, r1);
+        ntiles = max(0, (r1 - r0 + kTileRows - 1) / kTileRows);
+        nch = (P.dimp + KC - 1) / KC;
+        cs = cph = 0;
+        p_pass = p_c = p_j = 0;
+        Xb = P.X + (size_t)blk * P.nb * P.dimp;
+        for (size_t i = threadIdx.x; i < (size_t)NS * kTileRows * KC; i += kThreads)
+            stages[i] = 0.0;
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < NS; ++s)
+                mbar_init(&full[s], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == kProducerWarp * 32 && ntiles > 0)
+            for (int i = 0; i < NS; ++i)   // 2 * nch * ntiles >= NS always holds for nch >= 2
+                refill(i);
+    }
+
+    __device__ void drain()
+    {
+        if (ntiles == 0)
+            return;
+        int s = cs, ph = cph;
+        for (int i = 0; i < NS; ++i) {
+            mbar_wait(&full[s], (unsigned)ph);
+            if (++s == NS) {
+                s = 0;
+                ph ^= 1;
+            }
+        }
+    }
+
+    __device__ __forceinline__ int stage_wait()
+    {
+        const int s = cs;
+        mbar_wait(&full[s], (unsigned)cph);
+        if (++cs == NS) {
+            cs = 0;
+            cph ^= 1;
+        }
+        return s;
+    }
+
+    __device__ double eval(const double *xcur)
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int qd = lane & 3, gid = lane >> 2;
+        const int dimp = P.dimp, Cp = P.Cp;
+        double *Lb = P.R + (size_t)blk * P.nb * Cp;   // logits, then residuals, of this block's rows
+        const int *yb = P.y + (size_t)blk * P.nb;
+        const double *wb = P.w + (size_t)blk * P.nb;
+        const bool producer = threadIdx.x == kProducerWarp * 32;
+
+        // ---------------- pass 1: logits, chunk by chunk ----------------
+        for (int c = 0; c < nch; ++c) {
+            const int wc = width(c);
+            __syncthreads();  // previous chunk's W (or the solver's scratch) is no longer in use
+            for (int i = threadIdx.x; i < Cp * KC; i += kThreads) {
+                const int cc = i / KC, k = i - cc * KC;
+                smW[i] = (cc < P.C && k < wc) ? __ldcg(xcur + (size_t)cc * dimp + (size_t)c * KC + k) : 0.0;
+            }
+            __syncthreads();
+            const int nks = (wc + 3) >> 2;
+            const int ks0 = nks * min(warp, 8) / 8, ks1 = nks * min(warp + 1, 8) / 8;
+            // helper warps: the logits accumulated so far are fetched one tile ahead, so the L2
+            // round trip of the read-modify-write is off the per-tile critical path
+            double2 old_next = make_double2(0.0, 0.0);
+            const bool helper = warp >= 8 && warp - 8 < NCT;
+            if (helper && c > 0 && r0 + gid < r1)
+                old_next = *reinterpret_cast<const double2 *>(Lb + (size_t)(r0 + gid) * Cp + (warp - 8) * 8 + 2 * qd);
+            for (int j = 0; j <= ntiles; ++j) {
+                int s = -1;
+                if (j < ntiles)
+                    s = stage_wait();
+                if (warp < 8 && j < ntiles && !(P.dbg & 8)) {
+                    const double *tile = stages + (size_t)s * kTileRows * KC;
+                    double pa[NCT][4][2];
+#pragma unroll
+                    for (int ct = 0; ct < NCT; ++ct)
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4)
+                            pa[ct][q4][0] = pa[ct][q4][1] = 0.0;
+                    const double *xp = tile + (size_t)gid * KC + qd;
+                    const double *wp = smW + (size_t)gid * KC + qd;
+                    // the chain index must be a compile-time constant (registers, not local memory):
+                    // unrolled by 4 from this warp's first k-step, remainder handled below
+                    int ks = ks0;
+                    for (; ks + 3 < ks1; ks += 4) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const double xa = xp[4 * (ks + u)];
+#pragma unroll
+                            for (int ct = 0; ct < NCT; ++ct)
+                                dmma884(pa[ct][u], xa, wp[(size_t)ct * 8 * KC + 4 * (ks + u)]);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        if (ks + u < ks1) {
+                            const double xa = xp[4 * (ks + u)];
+#pragma unroll
+                            for (int ct = 0; ct < NCT; ++ct)
+                                dmma884(pa[ct][u], xa, wp[(size_t)ct * 8 * KC + 4 * (ks + u)]);
+                        }
+                    }
+                    double2 *dst = plog + ((size_t)(j & 1) * 8 + warp) * NCT * 32;
+#pragma unroll
+                    for (int ct = 0; ct < NCT; ++ct)
+                        dst[ct * 32 + lane] =
+                            make_double2((pa[ct][0][0] + pa[ct][1][0]) + (pa[ct][2][0] + pa[ct][3][0]),
+                                         (pa[ct][0][1] + pa[ct][1][1]) + (pa[ct][2][1] + pa[ct][3][1]));
+                } else if (helper && j >= 1 && !(P.dbg & 32)) {
+                    // helper warp of class tile ct: logits of tile j-1 += sum of the 8 partials
+                    const int ct = warp - 8;
+                    const int row = r0 + (j - 1) * kTileRows + gid;
+                    const double2 old = old_next;
+                    if (c > 0 && row + kTileRows < r1)
+                        old_next = *reinterpret_cast<const double2 *>(Lb + (size_t)(row + kTileRows) * Cp + ct * 8 + 2 * qd);
+                    const double2 *src = plog + (size_t)((j - 1) & 1) * 8 * NCT * 32;
+                    double2 v = src[ct * 32 + lane];
+#pragma unroll
+                    for (int w8 = 1; w8 < 8; ++w8) {
+                        const double2 pv = src[(w8 * NCT + ct) * 32 + lane];
+                        v.x += pv.x;
+                        v.y += pv.y;
+                    }
+                    if (row < r1) {
+                        double2 *lp = reinterpret_cast<double2 *>(Lb + (size_t)row * Cp + ct * 8 + 2 * qd);
+                        if (c > 0) {
+                            v.x += old.x;
+                            v.y += old.y;
+                        }
+                        *lp = v;
+                    }
+                }
+                __syncthreads();  // plog[j&1] complete; stage s and plog[(j-1)&1] free again
+                if (producer && j < ntiles)
+                    refill(s);
+            }
+        }
+
+        // ---------------- softmax over my rows: logits -> residuals, NLL ----------------
+        double facc = 0.0;
+        for (int row = r0 + threadIdx.x; row < r1; row += kThreads) {
+            double *lp = Lb + (size_t)row * Cp;
+            double mx = -INFINITY;
+            for (int cc = 0; cc < P.C; ++cc)
+                mx = fmax(mx, lp[cc]);
+            double den = 0.0;
+            for (int cc = 0; cc < P.C; ++cc)
+                den += exp(lp[cc] - mx);
+            const int cls = yb[row];
+            const double wi = wb[row];
+            facc -= wi * ((lp[cls] - mx) - log(den));
+            for (int cc = 0; cc < Cp; ++cc) {
+                double r = 0.0;
+                if (cc < P.C) {
+                    r = wi * (exp(lp[cc] - mx) / den);
+                    if (cc == cls)
+                        r -= wi;
+                }
+                lp[cc] = r;
+            }
+        }
+        __syncthreads();
+
+        // ---------------- pass 2: gradient, chunk by chunk ----------------
+        double *gp = P.gpart + ((size_t)blk * P.G + cta) * P.npad;
+        for (int c = 0; c < nch; ++c) {
+            const int wc = width(c);
+            const int ngroups = (wc + 15) >> 4;
+            double acc[NBG][2][NCT][2];
+#pragma unroll
+            for (int i = 0; i < NBG; ++i)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int ct = 0; ct < NCT; ++ct)
+                        acc[i][h][ct][0] = acc[i][h][ct][1] = 0.0;
+            // residual fragments R[row qd (+4)][class gid] are fetched one tile ahead (L2 latency)
+            double a_next[NCT][2];
+#pragma unroll
+            for (int ct = 0; ct < NCT; ++ct) {
+                a_next[ct][0] = (warp < 8 && r0 + qd < r1) ? Lb[(size_t)(r0 + qd) * Cp + ct * 8 + gid] : 0.0;
+                a_next[ct][1] = (warp < 8 && r0 + qd + 4 < r1) ? Lb[(size_t)(r0 + qd + 4) * Cp + ct * 8 + gid] : 0.0;
+            }
+            for (int j = 0; j < ntiles; ++j) {
+                const int s = stage_wait();
+                if (warp < 8 && !(P.dbg & 16)) {
+                    const double *tile = stages + (size_t)s * kTileRows * KC;
+                    const int rowa = r0 + (j + 1) * kTileRows + qd, rowb = rowa + 4;
+                    double a[NCT][2];
+#pragma unroll
+                    for (int ct = 0; ct < NCT; ++ct) {
+                        a[ct][0] = a_next[ct][0];
+                        a[ct][1] = a_next[ct][1];
+                        a_next[ct][0] = (rowa < r1) ? Lb[(size_t)rowa * Cp + ct * 8 + gid] : 0.0;
+                        a_next[ct][1] = (rowb < r1) ? Lb[(size_t)rowb * Cp + ct * 8 + gid] : 0.0;
+                    }
+                    double2 x0[NBG], x1[NBG];
+#pragma unroll
+                    for (int i = 0; i < NBG; ++i) {
+                        const int col = 16 * (warp + 8 * i) + 2 * gid;
+                        const int colc = (col < wc) ? col : 0;
+                        x0[i] = *reinterpret_cast<const double2 *>(tile + (size_t)qd * KC + colc);
+                        x1[i] = *reinterpret_cast<const double2 *>(tile + (size_t)(4 + qd) * KC + colc);
+                        if (col >= wc)
+                            x0[i] = x1[i] = make_double2(0.0, 0.0);
+                    }
+#pragma unroll
+                    for (int i = 0; i < NBG; ++i)
+#pragma unroll
+                        for (int ct = 0; ct < NCT; ++ct) {
+                            dmma884(acc[i][0][ct], a[ct][0], x0[i].x);
+                            dmma884(acc[i][1][ct], a[ct][0], x0[i].y);
+                            dmma884(acc[i][0][ct], a[ct][1], x1[i].x);
+                            dmma884(acc[i][1][ct], a[ct][1], x1[i].y);
+                        }
+                }
+                __syncthreads();
+                if (producer)
+                    refill(s);
+            }
+            if (warp < 8) {
+#pragma unroll
+                for (int i = 0; i < NBG; ++i) {
+                    const int cg = warp + 8 * i;
+                    const int col = 16 * cg + 4 * qd;
+                    if (cg < ngroups && col < wc) {
+#pragma unroll
+                        for (int ct = 0; ct < NCT; ++ct) {
+                            const int cc = ct * 8 + gid;
+                            if (cc < P.C) {
+                                double2 *dst = reinterpret_cast<double2 *>(gp + (size_t)cc * dimp +
+                                                                           (size_t)c * KC + col);
+                                __stcg(dst, make_double2(acc[i][0][ct][0], acc[i][1][ct][0]));
+                                __stcg(dst + 1, make_double2(acc[i][0][ct][1], acc[i][1][ct][1]));
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        return block_sum(facc, red);
     }
 };
 

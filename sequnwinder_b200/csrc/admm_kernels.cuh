@@ -35,6 +35,7 @@ __device__ __forceinline__ int ld_volatile_int(const int *p)
 // Evaluation modes of the x-update kernel:
 //   MODE 4  fused single pass over TMA-staged 8-row tiles, warp specialised (TileEvalWS):
 //           rows up to 672 columns, i.e. the k = 4..5 feature sets of the headline configs;
+//   MODE 6  two passes over column-chunked TMA-staged tiles (TileEvalChunk): any row length;
 //   MODE 1  two streaming passes from global memory, W in shared memory (admm_eval.cuh);
 //   MODE 2  the same with W read from global memory (row lengths beyond shared memory).
 template <int NCT, int MODE>
@@ -63,6 +64,10 @@ struct EvalSelect<NCT, 4> {
     typedef TileEvalWS<NCT, 24> type;
 };
 template <int NCT>
+struct EvalSelect<NCT, 6> {   // column-chunked TMA tiles: any row length
+    typedef TileEvalChunk<NCT> type;
+};
+template <int NCT>
 struct EvalSelect<NCT, 5> {   // MODE 4 with 21 k-steps per DMMA warp (rows <= 672 columns)
     typedef TileEvalWS<NCT, 21> type;
 };
@@ -76,6 +81,7 @@ struct BlockProblem {
     Eval &ev;
 
     __device__ double eval_partial(const double *x) { return ev.eval(x); }
+    __device__ int dbg() const { return P.dbg; }
 
     // gradient of coordinate k: data term reduced over the group's partials (fixed order), plus
     // the augmented Lagrangian term rho*(x - sm_x[par] - z + u_t) for w >= 1 (LOne.java:982-998);
@@ -84,7 +90,7 @@ struct BlockProblem {
     {
         const double *gp = P.gpart + (size_t)blk * P.G * P.npad + k;
         double s = 0.0;
-        for (int c0 = 0; c0 < P.G; c0 += 32) {
+        for (int c0 = 0; c0 < ((P.dbg & 1) ? 1 : P.G); c0 += 32) {
             double v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j)
@@ -94,7 +100,7 @@ struct BlockProblem {
                 s += v[j];
         }
         const int leaf = k / P.dimp, w = k - leaf * P.dimp;
-        if (w >= 1 && w < P.dim) {
+        if (w >= 1 && w < P.dim && !(P.dbg & 2)) {
             const int e0 = __ldg(P.leaf_edge_ptr + leaf), e1 = __ldg(P.leaf_edge_ptr + leaf + 1);
             for (int e = e0; e < e1; ++e) {
                 const int par = __ldg(P.edge_par + e);
@@ -470,7 +476,7 @@ admm_eval_kernel(AdmmDev P, TileSmemLayout L, double pho, double *f_out)
     ev.init(smem_raw, L, sm.red);
     BlockProblem<Eval> prob{P, blk, cta, pho, P.ut + (size_t)blk * P.upad, ev};
     double fpart = prob.eval_partial(xt);
-    if (MODE == 4 || MODE == 5) {
+    if (MODE == 4 || MODE == 5 || MODE == 6) {
         // further evaluations exercise the ring wrap-around / resident path; results must agree
         for (int rep = 0; rep < 2; ++rep) {
             __syncthreads();
@@ -496,6 +502,7 @@ struct RosenProblem {
     int n;
     __device__ double eval_partial(const double *) { return 0.0; }
     const double *x;
+    __device__ int dbg() const { return 0; }
     __device__ double grad_coord(int k, double, double &facc)
     {
         const int i = k >> 1;

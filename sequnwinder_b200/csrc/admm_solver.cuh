@@ -567,7 +567,7 @@ __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier 
         for (int k = k0 + threadIdx.x; k < k1; k += kThreads) {
             const double xk = __ldcg(ws.x + k);
             double dk = 0.0, go = 0.0, si[kLbfgsM], yi[kLbfgsM];
-            if (!first) {
+            if (!first && !(prob.dbg() & 4)) {
                 dk = ws.d[k];
                 go = ws.gold[k];
 #pragma unroll

@@ -67,6 +67,7 @@ struct AdmmDev {
     int upad;       // E * dimp
     int wstride;    // row stride of W in shared memory (bank-conflict free)
     int world;      // ranks
+    int dbg;        // timing experiments only (SQW_ADMM_DBG); 0 in production
     double ridge;   // lambda
 
     // ---- training data, block-major ----

@@ -106,6 +106,32 @@ def test_trainer_matches_oracle_fixed_iterations(oracle, cfg, n, mf, T, A, S):
     assert np.array_equal(pg, po)
 
 
+@pytest.mark.parametrize("cfg,n,T,A", [("cfg3", 2400, 8, 2),     # k=4..7: dim 10921, C=12 (column-chunked mode)
+                                         ("cfg4", 3400, 8, 2)])    # k=4..6: dim 2729, C=17 incl. Random leaf
+def test_long_rows_match_oracle(oracle, cfg, n, T, A):
+    """cfg-3 / cfg-4 feature shapes (rows far longer than shared memory) at reduced row counts."""
+    p = make_problem(cfg, n)
+    xo, smo, tr = oracle.lone_execute(p.x0, p.smx0, p.data, p.cls, p.weights, p.st, p.num_classes,
+                                      num_threads=T, admm_max_itr=A, nodes_max_itr=1, host_threads=8)
+    lo = run_gpu(p, T, A, 1)
+    assert np.array_equal(lo.log.nfev, tr.log_nfev[:, opt.java_block_order(T)])
+    assert np.abs(lo.getX() - xo).max() <= REL_TOL * np.abs(xo).max()
+    assert np.abs(lo.getsmX() - smo).max() <= REL_TOL * np.abs(smo).max()
+
+
+@pytest.mark.parametrize("mode", ["6", "1", "2"])
+def test_fallback_evaluation_modes_match_oracle(oracle, mode, monkeypatch):
+    """The more general evaluation paths (column-chunked TMA tiles, streaming) on a cfg-2 shape."""
+    monkeypatch.setenv("SQW_ADMM_EVAL_MODE", mode)
+    p = make_problem("cfg2", 4000)
+    T, A = 8, 3
+    xo, smo, tr = oracle.lone_execute(p.x0, p.smx0, p.data, p.cls, p.weights, p.st, p.num_classes,
+                                      num_threads=T, admm_max_itr=A, nodes_max_itr=1, host_threads=8)
+    lo = run_gpu(p, T, A, 1)
+    assert np.array_equal(lo.log.nfev, tr.log_nfev[:, opt.java_block_order(T)])
+    assert np.abs(lo.getX() - xo).max() <= REL_TOL * np.abs(xo).max()
+
+
 def test_rho_adaptation_and_convergence_paths(oracle):
     """A run long enough to double rho, converge an ADMM run early and finish the outer loop."""
     p = make_problem("cfg1", 400, max_features=200)

@@ -1,0 +1,12 @@
+import sys, numpy as np
+sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
+from sequnwinder_b200 import optimizer as opt
+from helpers import make_problem
+p = make_problem('cfg2', 20000)
+lo = opt.LOneCuda(p.x0.copy(), p.smx0.copy(), p.data)
+lo.setRidge(10.0); lo.setADMMmaxItrs(3); lo.setSeqUnwinderMaxIts(1)
+lo.setClassStructure(p.crs); lo.setClsMembership(p.cls); lo.setInstanceWeights(p.weights)
+lo.setNumClasses(p.num_classes); lo.setNumPredictors(p.data.shape[1]-1); lo.setPho(1.7); lo.set_numThreads(8)
+lo.setDebugMode(True)
+lo.execute()
+print('done', lo.stats.total_evals)
