@@ -343,13 +343,29 @@ struct TileEvalWS {
                             pa[ct][c][0] = pa[ct][c][1] = 0.0;
                     const double *xp = tile + (size_t)gid * dimp + qd;
                     if (W_REG) {
-                        double xa[KSW];  // wreg[u] is zero beyond ks1: clamped loads need no select
+                        // two halves (register budget: 168 per thread with 11 warps): the loads of
+                        // the second half are kept behind the first half's DMMAs by a compiler
+                        // barrier; wreg[u] is zero beyond ks1, so clamped loads need no select
+                        constexpr int H1 = (KSW + 1) / 2;
+                        {
+                            double xa[H1];
 #pragma unroll
-                        for (int u = 0; u < KSW; ++u)
-                            xa[u] = xp[4 * min(ks0 + u, ks1 - 1)];
+                            for (int u = 0; u < H1; ++u)
+                                xa[u] = xp[4 * min(ks0 + u, ks1 - 1)];
 #pragma unroll
-                        for (int u = 0; u < KSW; ++u)  // straight-line: skipping the padded k-steps
-                            dmma884(pa[0][u & 3], xa[u], wreg[u]);  // with branches measured slower
+                            for (int u = 0; u < H1; ++u)
+                                dmma884(pa[0][u & 3], xa[u], wreg[u]);
+                        }
+                        asm volatile("" ::: "memory");
+                        {
+                            double xa[KSW - H1];
+#pragma unroll
+                            for (int u = H1; u < KSW; ++u)
+                                xa[u - H1] = xp[4 * min(ks0 + u, ks1 - 1)];
+#pragma unroll
+                            for (int u = H1; u < KSW; ++u)
+                                dmma884(pa[0][u & 3], xa[u - H1], wreg[u]);
+                        }
                     } else {
                         const double *wp = smW + (size_t)gid * dimp + qd;
                         int ks = ks0;
