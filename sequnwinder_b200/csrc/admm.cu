@@ -81,6 +81,7 @@ static std::vector<int> java_thread_order(int T)
     return order;
 }
 
+constexpr int kNumPhases = 6;  // x-update launches per ADMM iteration (re-grouping points)
 constexpr int kRing = 8;       // Ctrl snapshots in flight
 constexpr int kLookahead = 3;  // iterations the host runs ahead of the snapshot it inspects
 
@@ -144,7 +145,7 @@ struct sqw_admm {
 
 namespace sqw {
 
-typedef void (*XKernel)(AdmmDev, TileSmemLayout);
+typedef void (*XKernel)(AdmmDev, TileSmemLayout, int, int);
 typedef void (*EKernel)(AdmmDev, TileSmemLayout, double, double *);
 
 static XKernel xupdate_kernel(int nct, int mode)
@@ -258,6 +259,8 @@ static int prepare(sqw_admm *h)
     const int max_useful = std::max(1, (D.nb + 7) / 8);
     G = std::min(G, max_useful);
     D.G = G;
+    D.Gmax = G * D.T_local;
+    D.nphase = kNumPhases;
 
     int rc;
 #define TRY(x)            \
@@ -293,12 +296,13 @@ static int prepare(sqw_admm *h)
     TRY(h->dalloc(&D.S, TL * kLbfgsM * D.npad));
     TRY(h->dalloc(&D.Y, TL * kLbfgsM * D.npad));
     TRY(h->dalloc(&D.R, TL * D.nb * D.Cp));
-    TRY(h->dalloc(&D.gpart, TL * D.G * D.npad));
-    TRY(h->dalloc(&D.spart, TL * D.G * kNumDots));
-    TRY(h->dalloc(&D.bar, TL * 32));
+    TRY(h->dalloc(&D.gpart, TL * D.Gmax * D.npad));
+    TRY(h->dalloc(&D.spart, TL * D.Gmax * kNumDots));
+    TRY(h->dalloc(&D.bstate, TL));
+    TRY(h->dalloc(&D.bar, TL * 32 * kNumPhases));
     TRY(h->dalloc(&D.nfev, TL));
     if (getenv("SQW_ADMM_PROFILE"))
-        TRY(h->dalloc(&D.prof, TL * D.G * 16));
+        TRY(h->dalloc(&D.prof, (size_t)D.Gmax * 16));
     TRY(h->dalloc(&D.sum1, (size_t)D.npad + D.upad));
     TRY(h->dalloc(&D.sum2, (size_t)D.E));
     TRY(h->dalloc(&D.edge_stats, (size_t)D.E * 4));
@@ -356,9 +360,29 @@ static int launch_xupdate(sqw_admm *h)
 {
     AdmmDev &D = h->dev;
     XKernel xk = xupdate_kernel(D.Cp / 8, h->eval_mode);
-    void *args[] = {&D, &h->layout};
-    SQW_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)xk, dim3(D.T_local * D.G), dim3(kThreads),
-                                               args, h->xupdate_smem, h->stream));
+    // evaluation caps of the phases (cumulative); the last phase runs every block to completion
+    static int caps[kNumPhases] = {8, 12, 16, 20, 26, 0x7fffffff};  // tuned at cfg-2 (mean 14.7, max 24 evaluations)
+    static bool caps_init = false;
+    if (!caps_init) {
+        caps_init = true;
+        if (const char *env = getenv("SQW_ADMM_CAPS")) {  // tuning hook: comma separated caps
+            int i = 0;
+            for (const char *q = env; *q && i < kNumPhases - 1; ++i) {
+                caps[i] = atoi(q);
+                while (*q && *q != ',')
+                    ++q;
+                if (*q == ',')
+                    ++q;
+            }
+        }
+    }
+    for (int ph = 0; ph < kNumPhases; ++ph) {
+        int phase = ph, cap = caps[ph];
+        void *args[] = {&D, &h->layout, &phase, &cap};
+        SQW_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)xk, dim3(D.Gmax), dim3(kThreads), args,
+                                                   h->xupdate_smem, h->stream));
+    }
+    h->stats.launches += kNumPhases - 1;
     return SQW_OK;
 }
 
@@ -907,7 +931,7 @@ int sqw_admm_execute(sqw_admm *h, double *x_inout, double *smx_inout)
     if ((rc = download_padded(h, D.smx, D.NN, D.dim, D.dimp, smx_inout)) != SQW_OK) return rc;
 
     if (D.prof) {
-        std::vector<long long> pr((size_t)D.T_local * D.G * 16);
+        std::vector<long long> pr((size_t)D.Gmax * 16);
         SQW_CUDA_CHECK(cudaMemcpy(pr.data(), D.prof, pr.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         const char *names[7] = {"eval", "barrier1", "reduce", "barrier2", "decide", "update", "barrier3"};
         for (int c : {0, D.G / 2, D.G - 1}) {
@@ -1005,7 +1029,7 @@ int sqw_admm_eval(sqw_admm *h, const double *cx, const double *smx, double pho, 
     SQW_CUDA_CHECK(cudaMemsetAsync(D.xt, 0, sizeof(double) * (size_t)D.T_local * D.Cp * D.dimp, st));
     SQW_CUDA_CHECK(cudaMemsetAsync(D.ut, 0, sizeof(double) * (size_t)D.T_local * D.upad, st));
     SQW_CUDA_CHECK(cudaMemsetAsync(D.z, 0, sizeof(double) * D.upad, st));
-    SQW_CUDA_CHECK(cudaMemsetAsync(D.bar, 0, sizeof(unsigned) * 32 * D.T_local, st));
+    SQW_CUDA_CHECK(cudaMemsetAsync(D.bar, 0, sizeof(unsigned) * 32 * D.T_local * kNumPhases, st));
     for (int b = 0; b < D.T_local; ++b)
         if ((rc = upload_padded(h, cx + (size_t)b * D.C * D.dim, D.C, D.dim, D.dimp,
                                 D.xt + (size_t)b * D.Cp * D.dimp)) != SQW_OK)
@@ -1017,7 +1041,7 @@ int sqw_admm_eval(sqw_admm *h, const double *cx, const double *smx, double pho, 
     SQW_CUDA_CHECK(cudaMemsetAsync(d_f, 0, sizeof(double) * D.T_local, st));
     EKernel ek = eval_kernel(D.Cp / 8, h->eval_mode);
     void *args[] = {&D, &h->layout, &pho, &d_f};
-    cudaError_t e = cudaLaunchCooperativeKernel((void *)ek, dim3(D.T_local * D.G), dim3(kThreads),
+    cudaError_t e = cudaLaunchCooperativeKernel((void *)ek, dim3(D.Gmax), dim3(kThreads),
                                                 args, h->xupdate_smem, st);
     if (e == cudaSuccess)
         e = cudaStreamSynchronize(st);

@@ -61,10 +61,10 @@ __device__ __forceinline__ double block_sum(double v, double *red)
 }
 
 // Rows [r0, r1) of the block handled by CTA `cta` of its group: whole 8-row tiles.
-__device__ __forceinline__ void cta_row_range(const AdmmDev &P, int cta, int &r0, int &r1)
+__device__ __forceinline__ void cta_row_range(const AdmmDev &P, int cta, int G, int &r0, int &r1)
 {
     const long long tiles = (P.nb + 7) / 8;
-    const long long t0 = tiles * cta / P.G, t1 = tiles * (cta + 1) / P.G;
+    const long long t0 = tiles * cta / G, t1 = tiles * (cta + 1) / G;
     r0 = (int)(t0 * 8);
     r1 = (int)min((long long)P.nb, t1 * 8);
 }
@@ -74,7 +74,7 @@ __device__ __forceinline__ void cta_row_range(const AdmmDev &P, int cta, int &r0
 // Returns the CTA's partial of the weighted NLL (valid in all threads) and writes the CTA's
 // partial gradient to P.gpart.
 template <int NCT, bool W_SMEM>
-__device__ double eval_data_term(const AdmmDev &P, int blk, int cta, const double *xcur,
+__device__ double eval_data_term(const AdmmDev &P, int blk, int cta, int G, const double *xcur,
                                  double *smW, double *red)
 {
     constexpr int NBG = (NCT == 1) ? 6 : (NCT == 2 ? 4 : 3);  // column groups per warp per batch
@@ -82,7 +82,7 @@ __device__ double eval_data_term(const AdmmDev &P, int blk, int cta, const doubl
     const int q = lane & 3, gid = lane >> 2;
     const int dimp = P.dimp, nb = P.nb, Cp = P.Cp;
     int r0, r1;
-    cta_row_range(P, cta, r0, r1);
+    cta_row_range(P, cta, G, r0, r1);
 
     const double *Xb = P.X + (size_t)blk * nb * dimp;
     const int *yb = P.y + (size_t)blk * nb;
@@ -174,7 +174,7 @@ __device__ double eval_data_term(const AdmmDev &P, int blk, int cta, const doubl
     // ---------------- pass 2: G = R^T X over the CTA's rows ----------------
     const int ngroups = (dimp + 15) >> 4;  // the last group is half wide when dimp = 8 (mod 16)
     const int nrq = (r1 - r0 + 3) >> 2;
-    double *gp = P.gpart + ((size_t)blk * P.G + cta) * P.npad;
+    double *gp = P.gpart + ((size_t)blk * P.Gmax + cta) * P.npad;
     for (int gb = 0; gb < ngroups; gb += kWarps * NBG) {
         double acc[NBG][2][NCT][2];
 #pragma unroll

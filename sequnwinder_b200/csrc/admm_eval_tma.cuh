@@ -139,7 +139,7 @@ template <int NCT, int KSW_ = 24>
 struct TileEvalWS {
     static constexpr int NBG = 6;  // 16-column groups per DMMA warp: rows up to 8*6*16 = 768 columns
     const AdmmDev &P;
-    int blk, cta;
+    int blk, cta, G;
     double *smW, *stages, *rs;
     double2 *plog;
     unsigned long long *full;
@@ -174,7 +174,7 @@ struct TileEvalWS {
         full = reinterpret_cast<unsigned long long *>(smem + L.bar_off);
         red = red_;
         NS = L.NS;
-        cta_row_range(P, cta, r0, r1);
+        cta_row_range(P, cta, G, r0, r1);
         ntiles = max(0, (r1 - r0 + kTileRows - 1) / kTileRows);
         resident = ntiles <= NS;
         cs = cph = 0;
@@ -509,7 +509,7 @@ struct TileEvalWS {
 
         // ---- partial gradient of this CTA
         if (warp < kDmmaWarps) {
-            double *gp = P.gpart + ((size_t)blk * P.G + cta) * P.npad;
+            double *gp = P.gpart + ((size_t)blk * P.Gmax + cta) * P.npad;
 #pragma unroll
             for (int i = 0; i < NBG; ++i) {
                 const int cg = warp + kDmmaWarps * i;
@@ -584,7 +584,7 @@ template <int NCT>
 struct TileEvalChunk {
     static constexpr int NBG = ChunkCfg<NCT>::NBG, KC = ChunkCfg<NCT>::KC, KSW = ChunkCfg<NCT>::KSW;
     const AdmmDev &P;
-    int blk, cta;
+    int blk, cta, G;
     double *smW, *stages;
     double2 *plog;
     unsigned long long *full;
@@ -627,7 +627,7 @@ struct TileEvalChunk {
         full = reinterpret_cast<unsigned long long *>(smem + L.bar_off);
         red = red_;
         NS = L.NS;
-        cta_row_range(P, cta, r0, r1);
+        cta_row_range(P, cta, G, r0, r1);
         ntiles = max(0, (r1 - r0 + kTileRows - 1) / kTileRows);
         nch = (P.dimp + KC - 1) / KC;
         cs = cph = 0;
@@ -797,7 +797,7 @@ struct TileEvalChunk {
         __syncthreads();
 
         // ---------------- pass 2: gradient, chunk by chunk ----------------
-        double *gp = P.gpart + ((size_t)blk * P.G + cta) * P.npad;
+        double *gp = P.gpart + ((size_t)blk * P.Gmax + cta) * P.npad;
         for (int c = 0; c < nch; ++c) {
             const int wc = width(c);
             const int ngroups = (wc + 15) >> 4;

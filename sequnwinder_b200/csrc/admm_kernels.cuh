@@ -41,7 +41,7 @@ __device__ __forceinline__ int ld_volatile_int(const int *p)
 template <int NCT, int MODE>
 struct StreamEval {
     const AdmmDev &P;
-    int blk, cta;
+    int blk, cta, G;
     double *smW, *red;
     __device__ void init(unsigned char *smem, const TileSmemLayout &, double *red_)
     {
@@ -50,7 +50,7 @@ struct StreamEval {
     }
     __device__ double eval(const double *x)
     {
-        return eval_data_term<NCT, MODE == 1>(P, blk, cta, x, smW, red);
+        return eval_data_term<NCT, MODE == 1>(P, blk, cta, G, x, smW, red);
     }
     __device__ void drain() {}
 };
@@ -75,7 +75,7 @@ struct EvalSelect<NCT, 5> {   // MODE 4 with 21 k-steps per DMMA warp (rows <= 6
 template <class Eval>
 struct BlockProblem {
     const AdmmDev &P;
-    int blk, cta;
+    int blk, cta, G;
     double pho;
     const double *ut;
     Eval &ev;
@@ -88,19 +88,19 @@ struct BlockProblem {
     // faug accumulates rho/2 * (...)^2 (LOne.java:1031-1047). xk = x[k].
     __device__ double grad_coord(int k, double xk, double &faug)
     {
-        const double *gp = P.gpart + (size_t)blk * P.G * P.npad + k;
+        const double *gp = P.gpart + (size_t)blk * P.Gmax * P.npad + k;
         double s = 0.0;
-        for (int c0 = 0; c0 < ((P.dbg & 1) ? 1 : P.G); c0 += 32) {
+        for (int c0 = 0; c0 < G; c0 += 32) {
             double v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-                v[j] = (c0 + j < P.G) ? __ldcg(gp + (size_t)(c0 + j) * P.npad) : 0.0;
+                v[j] = (c0 + j < G) ? __ldcg(gp + (size_t)(c0 + j) * P.npad) : 0.0;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
                 s += v[j];
         }
         const int leaf = k / P.dimp, w = k - leaf * P.dimp;
-        if (w >= 1 && w < P.dim && !(P.dbg & 2)) {
+        if (w >= 1 && w < P.dim) {
             const int e0 = __ldg(P.leaf_edge_ptr + leaf), e1 = __ldg(P.leaf_edge_ptr + leaf + 1);
             for (int e = e0; e < e1; ++e) {
                 const int par = __ldg(P.edge_par + e);
@@ -117,27 +117,60 @@ struct BlockProblem {
     }
 };
 
+// One "phase" of the x-update of an ADMM iteration. The host enqueues P.nphase of these per
+// iteration with growing evaluation caps: a block whose L-BFGS solve returns before the cap is
+// marked finished, and the next phase spreads ALL CTAs of the launch over the blocks that are still
+// iterating (the slowest block of an iteration needs 1.6x the mean number of evaluations at
+// cfg-2; with a fixed partition 39 % of the SM time was idle). The re-grouping points depend only
+// on evaluation counts, never on timing, so results stay reproducible run to run.
 template <int NCT, int MODE>
-__global__ void __launch_bounds__(kThreads, 1) admm_xupdate_kernel(AdmmDev P, TileSmemLayout L)
+__global__ void __launch_bounds__(kThreads, 1)
+admm_xupdate_kernel(AdmmDev P, TileSmemLayout L, int phase, int eval_cap)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ SolveSmem sm;
+    __shared__ int s_blk, s_G;
     if (ld_volatile_int(&P.ctrl->done) || ld_volatile_int(&P.ctrl->fatal))
         return;
-    const int blk = blockIdx.x / P.G, cta = blockIdx.x - blk * P.G;
+    if (threadIdx.x == 0) {
+        // the blocks still iterating, in local order; every CTA derives the same partition
+        int act = 0;
+        for (int b = 0; b < P.T_local; ++b)
+            act += P.bstate[b].finished ? 0 : 1;
+        s_blk = -1;
+        s_G = 0;
+        if (act > 0) {
+            const int G = (int)gridDim.x / act;
+            const int grp = (int)blockIdx.x / G;
+            if (grp < act) {
+                int seen = 0;
+                for (int b = 0; b < P.T_local; ++b)
+                    if (!P.bstate[b].finished && seen++ == grp)
+                        s_blk = b;
+                s_G = G;
+            }
+        }
+    }
+    __syncthreads();
+    const int blk = s_blk, G = s_G;
+    if (blk < 0)
+        return;
+    const int cta = (int)blockIdx.x % G;
+    BlockState *bs = P.bstate + blk;
+    const bool resume = bs->started != 0;
     const long long t_kernel0 = (P.prof && threadIdx.x == 0) ? sqw_now_ns() : 0;
     const double pho = P.ctrl->pho, fold = P.ctrl->fold;
     double *xt = P.xt + (size_t)blk * P.Cp * P.dimp;
     double *ut = P.ut + (size_t)blk * P.upad;
     sm.scratch = reinterpret_cast<double *>(smem_raw);
     typedef typename EvalSelect<NCT, MODE>::type Eval;
-    Eval ev{P, blk, cta};
+    Eval ev{P, blk, cta, G};
     ev.init(smem_raw, L, sm.red);
 
-    // u-update (LOne.java:833-861): x-hat_t = a x_t + (1-a) z_old - a sm_x[par];
-    // u_t += x-hat_t - z; u_t /= rho_fold.  Slice of the edge coordinates per CTA.
-    {
-        const int usl = ((P.upad + P.G - 1) / P.G + 15) & ~15;
+    if (!resume) {
+        // u-update (LOne.java:833-861): x-hat_t = a x_t + (1-a) z_old - a sm_x[par];
+        // u_t += x-hat_t - z; u_t /= rho_fold.  Slice of the edge coordinates per CTA.
+        const int usl = ((P.upad + G - 1) / G + 15) & ~15;
         const int u0 = min(P.upad, cta * usl), u1 = min(P.upad, u0 + usl);
         for (int i = u0 + threadIdx.x; i < u1; i += kThreads) {
             const int e = i / P.dimp, w = i - e * P.dimp;
@@ -150,10 +183,14 @@ __global__ void __launch_bounds__(kThreads, 1) admm_xupdate_kernel(AdmmDev P, Ti
             double u = ut[i] + xhat - P.z[i];
             ut[i] = u / fold;
         }
+    } else {
+        // resume an interrupted solve: scalar state back into shared memory
+        for (int i = threadIdx.x; i < (int)(sizeof(LbState) / sizeof(int)); i += kThreads)
+            reinterpret_cast<int *>(&sm.st)[i] = reinterpret_cast<const int *>(&bs->st)[i];
     }
 
-    GroupBarrier gb{P.bar + blk * 32, 0u, P.G};
-    BlockProblem<Eval> prob{P, blk, cta, pho, ut, ev};
+    GroupBarrier gb{P.bar + ((size_t)phase * P.T_local + blk) * 32, 0u, G};
+    BlockProblem<Eval> prob{P, blk, cta, G, pho, ut, ev};
     SolveWs ws;
     ws.n = P.npad;
     ws.x = xt;
@@ -163,28 +200,40 @@ __global__ void __launch_bounds__(kThreads, 1) admm_xupdate_kernel(AdmmDev P, Ti
     ws.wa = P.wa + (size_t)blk * P.npad;
     ws.S = P.S + (size_t)blk * kLbfgsM * P.npad;
     ws.Y = P.Y + (size_t)blk * kLbfgsM * P.npad;
-    ws.spart = P.spart + (size_t)blk * P.G * kNumDots;
-    ws.G = P.G;
+    ws.spart = P.spart + (size_t)blk * P.Gmax * kNumDots;
+    ws.G = G;
     ws.cta = cta;
     ws.prof = P.prof ? P.prof + (size_t)blockIdx.x * 16 : nullptr;
     int status = 0;
+    bool finished = false;
     const long long t_loop0 = (P.prof && threadIdx.x == 0) ? sqw_now_ns() : 0;
-    const int evals = lbfgs_group_solve(prob, ws, gb, sm, 0.1, 10e-16, status);  // LOne.java:874-875
+    const int evals = lbfgs_group_solve(prob, ws, gb, sm, 0.1, 10e-16, status, eval_cap, resume,
+                                        &finished);  // eps, xtol: LOne.java:874-875
     const long long t_loop1 = (P.prof && threadIdx.x == 0) ? sqw_now_ns() : 0;
     ev.drain();
     if (P.prof && threadIdx.x == 0) {
         long long *pf = P.prof + (size_t)blockIdx.x * 16;
-        // slots 4 and 12 of the evaluator table are unused: kernel prologue / epilogue time
-        pf[12] += t_loop0 - t_kernel0;
-        pf[4 + 8] += 0;
-        pf[8] += sqw_now_ns() - t_loop1;  // "Wstage" slot is ~0 in mode 4: reuse for the epilogue
+        pf[12] += t_loop0 - t_kernel0;       // kernel prologue
+        pf[8] += sqw_now_ns() - t_loop1;     // kernel epilogue
     }
-    if (cta == 0 && threadIdx.x == 0) {
-        P.nfev[blk] = evals;
-        if (status == 1)
-            atomicAdd(&P.ctrl->lbfgs_errors, 1);
-        if (status == 2)
-            atomicExch(&P.ctrl->fatal, 1);
+    if (cta == 0) {
+        // every CTA of the group holds the same scalar state; CTA 0 hands it to the next phase
+        __syncthreads();
+        if (!finished)
+            for (int i = threadIdx.x; i < (int)(sizeof(LbState) / sizeof(int)); i += kThreads)
+                reinterpret_cast<int *>(&bs->st)[i] = reinterpret_cast<const int *>(&sm.st)[i];
+        if (threadIdx.x == 0) {
+            bs->started = 1;
+            if (finished) {
+                bs->finished = 1;
+                bs->status = status;
+                P.nfev[blk] = evals;
+                if (status == 1)
+                    atomicAdd(&P.ctrl->lbfgs_errors, 1);
+                if (status == 2)
+                    atomicExch(&P.ctrl->fatal, 1);
+            }
+        }
     }
 }
 
@@ -324,7 +373,10 @@ __global__ void admm_decide_kernel(AdmmDev P)
     }
     for (int b = 0; b < P.T_local; ++b) {
         c->total_evals += P.nfev[b];
-        P.bar[b * 32] = 0u;
+        P.bstate[b].started = 0;
+        P.bstate[b].finished = 0;
+        for (int ph = 0; ph < P.nphase; ++ph)
+            P.bar[((size_t)ph * P.T_local + b) * 32] = 0u;
     }
     c->itr += 1;
     if (c->itr < c->max_itr) {
@@ -373,8 +425,11 @@ __global__ void __launch_bounds__(256) admm_begin_kernel(AdmmDev P, int outer, i
         P.ctrl->num_pass = 0;
         P.ctrl->num_pass_relaxed = 0;
         for (int b = 0; b < P.T_local; ++b) {
-            P.bar[b * 32] = 0u;
+            P.bstate[b].started = 0;
+            P.bstate[b].finished = 0;
             P.nfev[b] = 0;
+            for (int ph = 0; ph < P.nphase; ++ph)
+                P.bar[((size_t)ph * P.T_local + b) * 32] = 0u;
         }
     }
 }
@@ -472,9 +527,9 @@ admm_eval_kernel(AdmmDev P, TileSmemLayout L, double pho, double *f_out)
     double *xt = P.xt + (size_t)blk * P.Cp * P.dimp;
     GroupBarrier gb{P.bar + blk * 32, 0u, P.G};
     typedef typename EvalSelect<NCT, MODE>::type Eval;
-    Eval ev{P, blk, cta};
+    Eval ev{P, blk, cta, P.G};
     ev.init(smem_raw, L, sm.red);
-    BlockProblem<Eval> prob{P, blk, cta, pho, P.ut + (size_t)blk * P.upad, ev};
+    BlockProblem<Eval> prob{P, blk, cta, P.G, pho, P.ut + (size_t)blk * P.upad, ev};
     double fpart = prob.eval_partial(xt);
     if (MODE == 4 || MODE == 5 || MODE == 6) {
         // further evaluations exercise the ring wrap-around / resident path; results must agree

@@ -494,6 +494,16 @@ __device__ __forceinline__ void lbfgs_scalar_step(LbState &st, const double *dot
     dec.stp = st.stp;
 }
 
+// Solver state of one ADMM block carried from one x-update launch ("phase") of an ADMM iteration
+// to the next: the launches re-partition the CTAs among the blocks that are still iterating.
+struct BlockState {
+    LbState st;
+    int started;   // u-update done and first evaluation taken
+    int finished;  // L-BFGS returned (iflag 0 or line-search failure)
+    int status;    // 0 ok, 1 line search failed, 2 numeric trouble
+    int pad;
+};
+
 // ------------------------------------------------------------------ group solver
 // Workspace of one solve (all global memory, length n each; S/Y hold kLbfgsM vectors).
 struct SolveWs {
@@ -520,9 +530,13 @@ constexpr size_t kSolveScratchBytes = (size_t)kNumDots * (kThreads / 4) * sizeof
 //   double grad_coord(int k, double xk, double &faug)   reduced gradient of coordinate k (xk = x[k])
 // Runs to completion; returns the number of evaluations (identical in all CTAs). status: 0 ok,
 // 1 line search failed (ExceptionWithIflag in the reference), 2 numeric trouble.
+// eval_cap: stop (unfinished, state kept in sm.st) once that many evaluations have been made in
+// total; resume: sm.st already holds the state of an interrupted solve. finished tells which.
 template <class Problem>
 __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier &gb,
-                                 SolveSmem &sm, double eps, double xtol, int &status)
+                                 SolveSmem &sm, double eps, double xtol, int &status,
+                                 int eval_cap = 0x7fffffff, bool resume = false,
+                                 bool *finished = nullptr)
 {
     const int n = ws.n, G = ws.G, cta = ws.cta;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -530,12 +544,16 @@ __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier 
     const int sl = ((n + G - 1) / G + 15) & ~15;
     const int k0 = min(n, cta * sl), k1 = min(n, k0 + sl);
     LbState &st = sm.st;
-    for (int i = threadIdx.x; i < (int)(sizeof(LbState) / sizeof(int)); i += kThreads)
-        reinterpret_cast<int *>(&st)[i] = 0;
+    if (!resume) {
+        for (int i = threadIdx.x; i < (int)(sizeof(LbState) / sizeof(int)); i += kThreads)
+            reinterpret_cast<int *>(&st)[i] = 0;
+    }
     __syncthreads();
-    unsigned valid = 0;   // history slots to reduce against (excludes the slot being replaced)
-    int point = 0;        // slot y_new is written to
-    bool first = true;
+    // history slots to reduce against (excludes the slot being replaced) / slot y_new is written to
+    int point = resume ? st.point : 0;
+    unsigned valid = resume ? (hist_mask(st.point, st.hist) & ~(1u << st.point)) : 0u;
+    bool first = !resume;
+    bool done = false;
     status = 0;
 
     for (;;) {
@@ -659,10 +677,12 @@ __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier 
         const Decision &dec = sm.dec;
         if (sm.fatal) {
             status = 2;
+            done = true;
             break;
         }
         if (dec.action == ACT_FINISH || dec.action == ACT_FAIL) {
             status = (dec.action == ACT_FAIL) ? 1 : 0;
+            done = true;
             break;
         }
         if (dec.action == ACT_LINESEARCH) {
@@ -693,8 +713,12 @@ __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier 
         SQW_PROF(6)
         if (ws.prof && threadIdx.x == 0)
             ws.prof[7] += 1;
+        if (st.evals >= eval_cap)  // identical in every CTA; the trial point for the next
+            break;                 // evaluation is already in place
     }
 #undef SQW_PROF
+    if (finished)
+        *finished = done;
     int evals = 0;
     if (threadIdx.x == 0)
         sm.dec.hist = st.evals;

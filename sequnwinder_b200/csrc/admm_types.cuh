@@ -55,7 +55,9 @@ struct AdmmDev {
     // ---- sizes ----
     int T;          // total ADMM blocks (= --threads), fixes the numerics
     int T_local;    // blocks owned by this rank
-    int G;          // CTAs cooperating on one block in the x-update kernel
+    int G;          // CTAs per block while every local block is active (= Gmax / T_local)
+    int Gmax;       // CTAs of the x-update launch = slot stride of gpart / spart per block
+    int nphase;     // x-update launches per ADMM iteration (re-grouping points)
     int nb;         // rows per block = floor(N / T)
     int dim;        // numPredictors + 1
     int dimp;       // padded row length (multiple of 16)
@@ -103,9 +105,10 @@ struct AdmmDev {
     double *S;     // [T_local][m][npad]
     double *Y;     // [T_local][m][npad]
     double *R;     // [T_local][nb][Cp]   w_i * (softmax - onehot), between the two passes
-    double *gpart; // [T_local][G][npad]  per-CTA partial gradients
-    double *spart; // [T_local][G][kNumDots] per-CTA partial scalars
-    unsigned *bar; // [T_local][32] group barrier counters (one per 128-byte line)
+    double *gpart; // [T_local][Gmax][npad]  per-CTA partial gradients
+    double *spart; // [T_local][Gmax][kNumDots] per-CTA partial scalars
+    unsigned *bar; // [nphase][T_local][32] group barrier counters (one per 128-byte line)
+    struct BlockState *bstate; // [T_local] solver state carried between the phases of an iteration
     int *nfev;     // [T_local] evaluations done by the last x-update
     long long *prof; // optional [T_local*G][16] phase cycle counters (SQW_ADMM_PROFILE=1)
 
