@@ -335,12 +335,13 @@ def main():
 
     peak, peak_src = measured_peak_hbm()
     achieved = eval_bytes / eval_s / 1e9 if eval_s > 0 else 0.0
-    # DRAM traffic per x-update launch: ncu --set full capture of round 1 (profiles/
-    # r01_ncu_prof_xupdate_r1c.txt): 3.66 GB read + 0.46 GB written for the 35 evaluation rounds of
-    # the captured launch = 117.6 MB per evaluation round of 8 blocks (one pass over the 104 MB
-    # matrix + partial gradients), scaled to this run's average evaluation rounds per launch.
+    # DRAM traffic per x-update (the phased launches of one ADMM iteration taken together): ncu
+    # --set full capture of round 1 (profiles/r01_ncu_prof_xupdate_r1f.txt): 870.7 MB read + 73.3 MB
+    # written for the 8 evaluation rounds of the captured phase-0 launch = 118.0 MB per evaluation
+    # round of 8 blocks (one pass over the 104 MB matrix + partial gradients), scaled to this run's
+    # average evaluations per block and ADMM iteration.
     xupdate_launches = max(1, iters)
-    traffic = 117.6e6 * (evals / BLOCKS_PER_GPU / world) / xupdate_launches if world == 1 else None
+    traffic = 118.0e6 * (evals / BLOCKS_PER_GPU / world) / xupdate_launches if world == 1 else None
     kmer_bytes = n_sites * (LENGTH + 4 * kc.numK) * args.steps
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -367,6 +368,9 @@ def main():
                      "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "algorithmic_bytes_per_launch": eval_bytes / max(1, iters),
                      "peak_source": peak_src,
+                     "launch_unit": "one ADMM iteration's x-update = 6 phased cooperative launches "
+                                    "of admm_xupdate_kernel; achieved = algorithmic bytes / summed "
+                                    "CUDA-event durations of those launches",
                      "note": "algorithmic bytes = evaluations x (2 n_b dim 8 + 2 n_b C 8 + 12 n_b "
                              "+ 2 C dim 8) over the summed durations of the x-update kernels, which "
                              "also contain the L-BFGS phases"},

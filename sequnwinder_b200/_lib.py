@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsequnwinder_b200.so")
+# SQW_LIB_PATH: development hook to A/B two builds of the same library
+LIB_PATH = os.environ.get("SQW_LIB_PATH") or os.path.join(_HERE, "libsequnwinder_b200.so")
 
 SQW_OK = 0
 SQW_ERR_INVALID_ARG = -1

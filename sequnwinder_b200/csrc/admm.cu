@@ -221,7 +221,6 @@ static int prepare(sqw_admm *h)
     D.wstride = D.dimp;
     D.world = h->world;
     D.ridge = h->ridge;
-    D.dbg = getenv("SQW_ADMM_DBG") ? atoi(getenv("SQW_ADMM_DBG")) : 0;
     const int nct = D.Cp / 8;
     if ((long long)D.Cp * D.dimp * h->dev.T_local > (1ll << 31) - 1 || (long long)D.upad > (1 << 30))
         return set_error(SQW_ERR_UNSUPPORTED, "problem too large for 32-bit coordinate indices");
@@ -234,9 +233,9 @@ static int prepare(sqw_admm *h)
     if (mode == 4 || mode == 5 || mode == 6)
         h->xupdate_smem = h->layout.total;
     else if (mode == 1)
-        h->xupdate_smem = std::max(w_bytes, kSolveScratchBytes);
+        h->xupdate_smem = w_bytes;
     else
-        h->xupdate_smem = kSolveScratchBytes;
+        h->xupdate_smem = 0;
     XKernel xk = xupdate_kernel(nct, mode);
     EKernel ek = eval_kernel(nct, mode);
     SQW_CUDA_CHECK(cudaFuncSetAttribute(xk, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -302,7 +301,7 @@ static int prepare(sqw_admm *h)
     TRY(h->dalloc(&D.bar, TL * 32 * kNumPhases));
     TRY(h->dalloc(&D.nfev, TL));
     if (getenv("SQW_ADMM_PROFILE"))
-        TRY(h->dalloc(&D.prof, (size_t)D.Gmax * 16));
+        TRY(h->dalloc(&D.prof, (size_t)D.Gmax * kProfSlots * kNumPhases));
     TRY(h->dalloc(&D.sum1, (size_t)D.npad + D.upad));
     TRY(h->dalloc(&D.sum2, (size_t)D.E));
     TRY(h->dalloc(&D.edge_stats, (size_t)D.E * 4));
@@ -671,8 +670,9 @@ static int plan_blocks(sqw_admm *h, int64_t n_rows, int32_t dim, int32_t num_cla
     int dimp8 = (dim + 7) / 8 * 8;
     if (((dimp8 / 8) & 1) == 0)
         dimp8 += 8;
-    const size_t budget = (size_t)prop.sharedMemPerBlockOptin - 2048;  // static SolveSmem etc.
-    TileSmemLayout L = tile_smem_layout(Cp, dimp4, budget, kSolveScratchBytes);
+    const size_t budget = (size_t)prop.sharedMemPerBlockOptin - 8192;  // static SolveSmem etc.
+    // (one class tile: W lives in registers and the head of the layout is the solver's slice cache)
+    TileSmemLayout L = tile_smem_layout(Cp, dimp4, budget, nct == 1 ? kSolveSliceBytes : 0);
     // single-pass tiles: one class tile only (with more the register-resident gradient
     // accumulators of a whole row spill; the column-chunked mode 6 keeps them per chunk)
     const bool ws_ok = nct == 1 && L.NS >= 3 && L.NS <= 4 && (dimp4 + 15) / 16 <= kDmmaWarps * 6 &&
@@ -680,7 +680,7 @@ static int plan_blocks(sqw_admm *h, int64_t n_rows, int32_t dim, int32_t num_cla
     int mode = ws_ok ? 4 : ((size_t)Cp * dimp8 * 8 <= 160 * 1024 ? 1 : 2);
     if (mode == 4 && nct == 1 && (dimp4 / 4 + kDmmaWarps - 1) / kDmmaWarps <= 21)
         mode = 5;  // same kernel with 21 instead of 24 unrolled k-steps per DMMA warp
-    TileSmemLayout Lc = chunk_smem_layout(Cp, budget, kSolveScratchBytes);
+    TileSmemLayout Lc = chunk_smem_layout(Cp, budget, 0);
     if (mode != 4 && mode != 5 && Lc.NS >= 2)
         mode = 6;  // long rows: column-chunked TMA tiles instead of per-thread global loads
     if (const char *env = getenv("SQW_ADMM_EVAL_MODE")) {  // test hook: force a more general path
@@ -931,19 +931,34 @@ int sqw_admm_execute(sqw_admm *h, double *x_inout, double *smx_inout)
     if ((rc = download_padded(h, D.smx, D.NN, D.dim, D.dimp, smx_inout)) != SQW_OK) return rc;
 
     if (D.prof) {
-        std::vector<long long> pr((size_t)D.Gmax * 16);
+        // thread 0 of CTA 0 (first CTA of the first unfinished block), per phase of the x-update
+        std::vector<long long> pr((size_t)D.Gmax * kProfSlots * kNumPhases);
         SQW_CUDA_CHECK(cudaMemcpy(pr.data(), D.prof, pr.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         const char *names[7] = {"eval", "barrier1", "reduce", "barrier2", "decide", "update", "barrier3"};
-        for (int c : {0, D.G / 2, D.G - 1}) {
-            const long long *q = &pr[(size_t)c * 16];
-            fprintf(stderr, "[sqw profile] block 0 cta %d: evals %lld;", c, q[7]);
+        const char *en[8] = {"kernel_epilogue", "tilewait", "pass1", "rr_wait", "kernel_prologue", "pass2",
+                             "free_arrive", "combine"};
+        const char *sn[6] = {"R:loads+gradient", "R:products+shuffles", "R:sync", "R:warp sums+store",
+                             "S:partials", "S:scalar step"};
+        for (int ph = 0; ph < kNumPhases; ++ph) {
+            const long long *q = &pr[(size_t)ph * D.Gmax * kProfSlots];
+            if (!q[7])
+                continue;
+            fprintf(stderr, "[sqw profile] phase %d cta 0: evals %lld;", ph, q[7]);
             for (int i = 0; i < 7; ++i)
-                fprintf(stderr, " %s %.0f ns", names[i], q[7] ? (double)q[i] / q[7] : 0.0);
-            const char *en[8] = {"kernel_epilogue", "tilewait", "pass1", "rr_wait", "kernel_prologue", "pass2", "free_arrive", "combine"};
+                fprintf(stderr, " %s %.0f ns", names[i], (double)q[i] / q[7]);
             fprintf(stderr, "\n[sqw profile]    eval breakdown per eval (ns):");
             for (int i = 0; i < 8; ++i)
-                fprintf(stderr, " %s %.0f", en[i], q[7] ? (double)q[8 + i] / q[7] : 0.0);
+                fprintf(stderr, " %s %.0f", en[i], (double)q[8 + i] / q[7]);
+            fprintf(stderr, "\n[sqw profile]    solver breakdown per eval (ns):");
+            for (int i = 0; i < 6; ++i)
+                fprintf(stderr, " %s %.0f", sn[i], (double)q[16 + i] / q[7]);
             fprintf(stderr, "\n");
+            if (q[31]) {
+                fprintf(stderr, "[sqw profile]    first trip of a launch (%lld launches, ns):", q[31]);
+                for (int i = 0; i < 7; ++i)
+                    fprintf(stderr, " %s %.0f", names[i], (double)q[24 + i] / q[31]);
+                fprintf(stderr, "\n");
+            }
         }
         SQW_CUDA_CHECK(cudaMemset(D.prof, 0, pr.size() * sizeof(long long)));
     }
@@ -1090,14 +1105,15 @@ int sqw_lbfgs_rosenbrock(int32_t n, double *x_inout, double eps, int32_t *nfev_o
     ws.G = G;
     ws.cta = 0;
     ws.prof = nullptr;
+    ws.slice = nullptr;  // set by the kernel
     SQW_CUDA_CHECK(cudaMemcpy(ws.x, x_inout, nv * sizeof(double), cudaMemcpyHostToDevice));
     void *args[] = {&ws, &bar, &eps, &out};
     cudaError_t e = cudaFuncSetAttribute(lbfgs_rosenbrock_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kSolveScratchBytes);
+                                         (int)kSolveSliceBytes);
     if (e == cudaSuccess)
         e = cudaLaunchCooperativeKernel((void *)lbfgs_rosenbrock_kernel, dim3(G), dim3(kThreads), args,
-                                        kSolveScratchBytes, 0);
+                                        kSolveSliceBytes, 0);
     if (e == cudaSuccess)
         e = cudaDeviceSynchronize();
     int res[2] = {0, 0};

@@ -229,7 +229,7 @@ __device__ double eval_data_term(const AdmmDev &P, int blk, int cta, int G, cons
             }
         }
     }
-    return fsum;
+    return threadIdx.x == 0 ? fsum : 0.0;  // per-thread partial whose CTA sum is fsum
 }
 
 }  // namespace sqw

@@ -67,7 +67,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
 
 // Shared-memory carve-up of the x-update kernel (fast path); offsets in bytes.
 struct TileSmemLayout {
-    size_t w_off, w_bytes;         // W [Cp][dimp] (C > 8 only); doubles as the solver's reduce scratch
+    size_t w_off, w_bytes;         // W [Cp][dimp] (C > 8 only); with one class tile: the solver's slice cache
     size_t stage_off, stage_bytes; // NS stages of kTileRows x dimp doubles
     size_t plog_off;               // [kWarps][NCT][32] double2 partial logits
     size_t rs_off;                 // [kWarps][NCT][64] residual fragments
@@ -180,7 +180,7 @@ struct TileEvalWS {
         cs = cph = 0;
         pt = 0;
         evals_done = 0;
-        prof = P.prof ? P.prof + (size_t)blockIdx.x * 16 + 8 : nullptr;
+        prof = nullptr;
         Xb = P.X + (size_t)blk * P.nb * P.dimp;
         for (size_t i = threadIdx.x; i < (size_t)NS * kTileRows * P.dimp; i += kThreads)
             stages[i] = 0.0;
@@ -199,6 +199,8 @@ struct TileEvalWS {
             pt = resident ? 0 : (NS == ntiles ? 0 : NS);
         }
     }
+
+    __device__ void set_profile(long long *p) { prof = p; }
 
     __device__ void drain()
     {
@@ -505,9 +507,12 @@ struct TileEvalWS {
             cs = adv % NS;
         }
         evals_done++;
+#if defined(SQW_EVAL_EPILOGUE_SYNC)
         __syncthreads();
+#endif
 
-        // ---- partial gradient of this CTA
+        // ---- partial gradient of this CTA: every DMMA warp stores its accumulators as soon as its
+        // last tile is done (no CTA-wide synchronisation here; the caller's barrier follows)
         if (warp < kDmmaWarps) {
             double *gp = P.gpart + ((size_t)blk * P.Gmax + cta) * P.npad;
 #pragma unroll
@@ -527,10 +532,9 @@ struct TileEvalWS {
                 }
             }
         }
-        const double fs = block_sum(facc, red);
         SQW_EPROF(7)
 #undef SQW_EPROF
-        return fs;
+        return facc;  // per-thread NLL partial (non-zero in the softmax warps only)
     }
 };
 
@@ -648,6 +652,8 @@ struct TileEvalChunk {
                 refill(i);
     }
 
+    __device__ void set_profile(long long *) {}
+
     __device__ void drain()
     {
         if (ntiles == 0)
@@ -704,7 +710,7 @@ struct TileEvalChunk {
                 int s = -1;
                 if (j < ntiles)
                     s = stage_wait();
-                if (warp < 8 && j < ntiles && !(P.dbg & 8)) {
+                if (warp < 8 && j < ntiles) {
                     const double *tile = stages + (size_t)s * kTileRows * KC;
                     double pa[NCT][4][2];
 #pragma unroll
@@ -741,7 +747,7 @@ struct TileEvalChunk {
                         dst[ct * 32 + lane] =
                             make_double2((pa[ct][0][0] + pa[ct][1][0]) + (pa[ct][2][0] + pa[ct][3][0]),
                                          (pa[ct][0][1] + pa[ct][1][1]) + (pa[ct][2][1] + pa[ct][3][1]));
-                } else if (helper && j >= 1 && !(P.dbg & 32)) {
+                } else if (helper && j >= 1) {
                     // helper warp of class tile ct: logits of tile j-1 += sum of the 8 partials
                     const int ct = warp - 8;
                     const int row = r0 + (j - 1) * kTileRows + gid;
@@ -818,7 +824,7 @@ struct TileEvalChunk {
             }
             for (int j = 0; j < ntiles; ++j) {
                 const int s = stage_wait();
-                if (warp < 8 && !(P.dbg & 16)) {
+                if (warp < 8) {
                     const double *tile = stages + (size_t)s * kTileRows * KC;
                     const int rowa = r0 + (j + 1) * kTileRows + qd, rowb = rowa + 4;
                     double a[NCT][2];
@@ -873,7 +879,8 @@ struct TileEvalChunk {
                 }
             }
         }
-        return block_sum(facc, red);
+        const double fs = block_sum(facc, red);
+        return threadIdx.x == 0 ? fs : 0.0;  // per-thread partial whose CTA sum is fs
     }
 };
 

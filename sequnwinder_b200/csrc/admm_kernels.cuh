@@ -52,6 +52,7 @@ struct StreamEval {
     {
         return eval_data_term<NCT, MODE == 1>(P, blk, cta, G, x, smW, red);
     }
+    __device__ void set_profile(long long *) {}
     __device__ void drain() {}
 };
 
@@ -72,6 +73,30 @@ struct EvalSelect<NCT, 5> {   // MODE 4 with 21 k-steps per DMMA warp (rows <= 6
     typedef TileEvalWS<NCT, 21> type;
 };
 
+// Shared-memory copy of the (tiny) leaf -> edge -> parent tables: the augmented term of every
+// coordinate walks them, and from global memory each hop is a dependent L1/L2 round trip.
+struct StructCache {
+    static constexpr int kMaxLeaves = 64, kMaxEdges = 256;
+    int lep[kMaxLeaves + 1];
+    int epar[kMaxEdges];
+    const int *lep_p, *epar_p;
+    // all threads; followed by a __syncthreads before first use (the evaluator's init has one)
+    __device__ void init(const AdmmDev &P)
+    {
+        const bool fits = P.C <= kMaxLeaves && P.E <= kMaxEdges;
+        if (fits) {
+            for (int i = threadIdx.x; i <= P.C; i += blockDim.x)
+                lep[i] = P.leaf_edge_ptr[i];
+            for (int i = threadIdx.x; i < P.E; i += blockDim.x)
+                epar[i] = P.edge_par[i];
+        }
+        if (threadIdx.x == 0) {
+            lep_p = fits ? lep : P.leaf_edge_ptr;
+            epar_p = fits ? epar : P.edge_par;
+        }
+    }
+};
+
 template <class Eval>
 struct BlockProblem {
     const AdmmDev &P;
@@ -79,41 +104,89 @@ struct BlockProblem {
     double pho;
     const double *ut;
     Eval &ev;
+    const int *lep;    // leaf_edge_ptr / edge_par: shared-memory copies when they fit (StructCache)
+    const int *epar;
 
     __device__ double eval_partial(const double *x) { return ev.eval(x); }
-    __device__ int dbg() const { return P.dbg; }
 
-    // gradient of coordinate k: data term reduced over the group's partials (fixed order), plus
-    // the augmented Lagrangian term rho*(x - sm_x[par] - z + u_t) for w >= 1 (LOne.java:982-998);
-    // faug accumulates rho/2 * (...)^2 (LOne.java:1031-1047). xk = x[k].
-    __device__ double grad_coord(int k, double xk, double &faug)
+    // data term of coordinate k reduced over the group's phase-E partials (fixed order), in two
+    // halves so that the caller can put other loads behind the first batch: data_issue starts the
+    // loads of the first kBatch partials, data_finish sums them and any further batches.
+    // 24 covers a group of 18 (8 blocks on 148 SMs) in one L2 round trip.
+    static constexpr int kBatch = 24;
+    __device__ void data_issue(int k, double (&v)[kBatch])
+    {
+        const double *gp = P.gpart + (size_t)blk * P.Gmax * P.npad + k;
+#pragma unroll
+        for (int j = 0; j < kBatch; ++j)
+            v[j] = (j < G) ? __ldcg(gp + (size_t)j * P.npad) : 0.0;
+    }
+    __device__ double data_finish(int k, double (&v)[kBatch])
     {
         const double *gp = P.gpart + (size_t)blk * P.Gmax * P.npad + k;
         double s = 0.0;
-        for (int c0 = 0; c0 < G; c0 += 32) {
-            double v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
+        for (int j = 0; j < kBatch; ++j)
+            s += v[j];
+        for (int c0 = kBatch; c0 < G; c0 += kBatch) {
+#pragma unroll
+            for (int j = 0; j < kBatch; ++j)
                 v[j] = (c0 + j < G) ? __ldcg(gp + (size_t)(c0 + j) * P.npad) : 0.0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
+            for (int j = 0; j < kBatch; ++j)
                 s += v[j];
         }
+        return s;
+    }
+    __device__ double data_term(int k)
+    {
+        double v[kBatch];
+        data_issue(k, v);
+        return data_finish(k, v);
+    }
+
+    // augmented Lagrangian term rho*(x - sm_x[par] - z + u_t) of coordinate k for w >= 1
+    // (LOne.java:982-998); faug accumulates rho/2 * (...)^2 (LOne.java:1031-1047). xk = x[k].
+    // Reads only x and data that is constant once the u-update is complete.
+    __device__ double aug_term(int k, double xk, double &faug)
+    {
+        double s = 0.0;
         const int leaf = k / P.dimp, w = k - leaf * P.dimp;
         if (w >= 1 && w < P.dim) {
-            const int e0 = __ldg(P.leaf_edge_ptr + leaf), e1 = __ldg(P.leaf_edge_ptr + leaf + 1);
-            for (int e = e0; e < e1; ++e) {
-                const int par = __ldg(P.edge_par + e);
-                const size_t o = (size_t)e * P.dimp + w;
+            const int e0 = lep[leaf], e1 = lep[leaf + 1];
+            // two edges per trip with every load issued before the first use: the term costs one
+            // L2 round trip for the usual one or two parents per leaf (same arithmetic order)
+            for (int e = e0; e < e1; e += 2) {
+                const bool two = e + 1 < e1;
+                const int par0 = epar[e], par1 = two ? epar[e + 1] : -1;
+                const size_t o0 = (size_t)e * P.dimp + w, o1 = two ? o0 + P.dimp : o0;
+                const double sx0 = (par0 >= 0) ? __ldg(P.smx + (size_t)par0 * P.dimp + w) : 0.0;
+                const double sx1 = (par1 >= 0) ? __ldg(P.smx + (size_t)par1 * P.dimp + w) : 0.0;
+                const double z0 = __ldg(P.z + o0), z1 = __ldg(P.z + o1);
+                const double u0 = __ldcg(ut + o0), u1 = __ldcg(ut + o1);
                 double v = xk;
-                if (par >= 0)
-                    v -= __ldg(P.smx + (size_t)par * P.dimp + w);
-                v = (v - __ldg(P.z + o)) + __ldcg(ut + o);
+                if (par0 >= 0)
+                    v -= sx0;
+                v = (v - z0) + u0;
                 s += pho * v;
                 faug += (pho / 2) * v * v;
+                if (two) {
+                    v = xk;
+                    if (par1 >= 0)
+                        v -= sx1;
+                    v = (v - z1) + u1;
+                    s += pho * v;
+                    faug += (pho / 2) * v * v;
+                }
             }
         }
         return s;
+    }
+
+    __device__ double grad_coord(int k, double xk, double &faug)
+    {
+        const double a = aug_term(k, xk, faug);
+        return data_term(k) + a;
     }
 };
 
@@ -132,6 +205,15 @@ admm_xupdate_kernel(AdmmDev P, TileSmemLayout L, int phase, int eval_cap)
     __shared__ int s_blk, s_G;
     if (ld_volatile_int(&P.ctrl->done) || ld_volatile_int(&P.ctrl->fatal))
         return;
+    // SQW_ADMM_PROFILE: thread 0 accumulates its time stamps in shared memory (a global
+    // read-modify-write per stamp would put an L2 round trip into the next interval) and adds them
+    // to the per-phase global counters once, at the end of the launch
+    __shared__ long long s_prof[kProfSlots];
+    if (P.prof) {
+        P.prof += ((size_t)phase * gridDim.x + blockIdx.x) * kProfSlots;
+        if (threadIdx.x < kProfSlots)
+            s_prof[threadIdx.x] = 0;
+    }
     if (threadIdx.x == 0) {
         // the blocks still iterating, in local order; every CTA derives the same partition
         int act = 0;
@@ -162,10 +244,12 @@ admm_xupdate_kernel(AdmmDev P, TileSmemLayout L, int phase, int eval_cap)
     const double pho = P.ctrl->pho, fold = P.ctrl->fold;
     double *xt = P.xt + (size_t)blk * P.Cp * P.dimp;
     double *ut = P.ut + (size_t)blk * P.upad;
-    sm.scratch = reinterpret_cast<double *>(smem_raw);
+    __shared__ StructCache sc;
+    sc.init(P);
     typedef typename EvalSelect<NCT, MODE>::type Eval;
     Eval ev{P, blk, cta, G};
     ev.init(smem_raw, L, sm.red);
+    ev.set_profile(P.prof ? s_prof + 8 : nullptr);
 
     if (!resume) {
         // u-update (LOne.java:833-861): x-hat_t = a x_t + (1-a) z_old - a sm_x[par];
@@ -190,7 +274,8 @@ admm_xupdate_kernel(AdmmDev P, TileSmemLayout L, int phase, int eval_cap)
     }
 
     GroupBarrier gb{P.bar + ((size_t)phase * P.T_local + blk) * 32, 0u, G};
-    BlockProblem<Eval> prob{P, blk, cta, G, pho, ut, ev};
+    __syncthreads();
+    BlockProblem<Eval> prob{P, blk, cta, G, pho, ut, ev, sc.lep_p, sc.epar_p};
     SolveWs ws;
     ws.n = P.npad;
     ws.x = xt;
@@ -203,7 +288,9 @@ admm_xupdate_kernel(AdmmDev P, TileSmemLayout L, int phase, int eval_cap)
     ws.spart = P.spart + (size_t)blk * P.Gmax * kNumDots;
     ws.G = G;
     ws.cta = cta;
-    ws.prof = P.prof ? P.prof + (size_t)blockIdx.x * 16 : nullptr;
+    ws.prof = P.prof ? s_prof : nullptr;
+    // modes 4/5 keep W in registers: the head of the dynamic shared memory is the slice cache
+    ws.slice = ((MODE == 4 || MODE == 5) && NCT == 1) ? reinterpret_cast<double *>(smem_raw) : nullptr;
     int status = 0;
     bool finished = false;
     const long long t_loop0 = (P.prof && threadIdx.x == 0) ? sqw_now_ns() : 0;
@@ -212,9 +299,10 @@ admm_xupdate_kernel(AdmmDev P, TileSmemLayout L, int phase, int eval_cap)
     const long long t_loop1 = (P.prof && threadIdx.x == 0) ? sqw_now_ns() : 0;
     ev.drain();
     if (P.prof && threadIdx.x == 0) {
-        long long *pf = P.prof + (size_t)blockIdx.x * 16;
-        pf[12] += t_loop0 - t_kernel0;       // kernel prologue
-        pf[8] += sqw_now_ns() - t_loop1;     // kernel epilogue
+        s_prof[12] += t_loop0 - t_kernel0;       // kernel prologue
+        s_prof[8] += sqw_now_ns() - t_loop1;     // kernel epilogue
+        for (int i = 0; i < kProfSlots; ++i)
+            P.prof[i] += s_prof[i];
     }
     if (cta == 0) {
         // every CTA of the group holds the same scalar state; CTA 0 hands it to the next phase
@@ -529,7 +617,8 @@ admm_eval_kernel(AdmmDev P, TileSmemLayout L, double pho, double *f_out)
     typedef typename EvalSelect<NCT, MODE>::type Eval;
     Eval ev{P, blk, cta, P.G};
     ev.init(smem_raw, L, sm.red);
-    BlockProblem<Eval> prob{P, blk, cta, P.G, pho, P.ut + (size_t)blk * P.upad, ev};
+    BlockProblem<Eval> prob{P, blk, cta, P.G, pho, P.ut + (size_t)blk * P.upad, ev,
+                            P.leaf_edge_ptr, P.edge_par};
     double fpart = prob.eval_partial(xt);
     if (MODE == 4 || MODE == 5 || MODE == 6) {
         // further evaluations exercise the ring wrap-around / resident path; results must agree
@@ -540,6 +629,7 @@ admm_eval_kernel(AdmmDev P, TileSmemLayout L, double pho, double *f_out)
                 fpart = nan("");
         }
     }
+    fpart = block_sum(fpart, sm.red);
     ev.drain();
     gb.sync();
     const int n = P.npad;
@@ -557,8 +647,10 @@ struct RosenProblem {
     int n;
     __device__ double eval_partial(const double *) { return 0.0; }
     const double *x;
-    __device__ int dbg() const { return 0; }
-    __device__ double grad_coord(int k, double, double &facc)
+    static constexpr int kBatch = 1;
+    __device__ void data_issue(int, double (&)[kBatch]) {}
+    __device__ double data_finish(int, double (&)[kBatch]) { return 0.0; }
+    __device__ double aug_term(int k, double, double &facc)
     {
         const int i = k >> 1;
         const double a = __ldcg(x + 2 * i), b = __ldcg(x + 2 * i + 1);
@@ -575,8 +667,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 lbfgs_rosenbrock_kernel(SolveWs ws, unsigned *bar, double eps, int *out)
 {
     __shared__ SolveSmem sm;
-    extern __shared__ __align__(16) double rosen_scratch[];
-    sm.scratch = rosen_scratch;
+    extern __shared__ __align__(16) double rosen_slice[];
+    ws.slice = rosen_slice;
     RosenProblem prob{ws.n, ws.x};
     ws.cta = blockIdx.x;
     GroupBarrier gb{bar, 0u, ws.G};

@@ -32,18 +32,30 @@ struct GroupBarrier {
     unsigned *ctr;
     unsigned target;
     int G;
-    __device__ __forceinline__ void sync()
+    // Split form: arrive() publishes this CTA's writes, wait() returns once all G CTAs have
+    // arrived. Loads that do not depend on the other CTAs' current phase go in between, so their
+    // L2 latency overlaps the barrier's.
+    __device__ __forceinline__ void arrive()
     {
         target += (unsigned)G;
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (threadIdx.x == 0)
             asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+    }
+    __device__ __forceinline__ void wait()
+    {
+        if (threadIdx.x == 0) {
             unsigned v;
             do {
                 asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
             } while (v < target);
         }
         __syncthreads();
+    }
+    __device__ __forceinline__ void sync()
+    {
+        arrive();
+        wait();
     }
 };
 
@@ -345,7 +357,15 @@ __device__ __forceinline__ unsigned hist_mask(int point, int hist)
 // The scalar step after an evaluation whose reduced scalars are dots[] (shared memory). Mirrors
 // the tail of LBFGS.lbfgs (LBFGS.java:531-590) followed by the head of its next loop trip
 // (:407-527), with the two-loop recursion evaluated on the Gram matrices.
-__device__ __forceinline__ void lbfgs_scalar_step(LbState &st, const double *dots, double eps,
+#ifndef SQW_SCALAR_NOINLINE
+#define SQW_SCALAR_NOINLINE 0
+#endif
+#if SQW_SCALAR_NOINLINE
+__device__ __noinline__ void lbfgs_scalar_step(
+#else
+__device__ __forceinline__ void lbfgs_scalar_step(
+#endif
+    LbState &st, const double *dots, double eps,
                                                   double xtol, Decision &dec, int &fatal, bool first)
 {
     constexpr int m = kLbfgsM;
@@ -505,33 +525,76 @@ struct BlockState {
 };
 
 // ------------------------------------------------------------------ group solver
-// Workspace of one solve (all global memory, length n each; S/Y hold kLbfgsM vectors).
+// Workspace of one solve (global memory, length n each; S/Y hold kLbfgsM vectors).
 struct SolveWs {
     int n;
     double *x;     // in: start point, out: result (trial point during the solve)
     double *g, *gold, *d, *wa, *S, *Y;
     double *spart; // [G][kNumDots]
     int G, cta;
-    long long *prof; // optional [8] per CTA: cycles in E, barrier1, R, barrier2, S, update, barrier3, evals
+    long long *prof; // optional (shared memory): ns in E, barrier1, R, barrier2, S, U, barrier3, evals, ...
+    double *slice;   // optional shared memory, kSliceVectors * kSliceCap doubles: the CTA's coordinate
+                     // slice of x, d, g_old, wa, S, Y stays on chip for the whole launch
 };
+
+constexpr int kSliceCap = 320;                       // coordinates per CTA the slice cache holds
+constexpr int kSliceVectors = 4 + 2 * kLbfgsM;       // x, d, g_old, wa, S[m], Y[m]
+constexpr size_t kSolveSliceBytes = (size_t)kSliceVectors * kSliceCap * sizeof(double);
 
 struct SolveSmem {
     double dots[kNumDots];
     double red[kWarps];
+    double wred[kWarps][kNumDots];  // per-warp totals of the 32 scalar partials
     Decision dec;
     LbState st;       // scalar solver state: shared memory keeps it out of every thread's registers
     int fatal;
-    double *scratch;  // >= kNumDots * (kThreads / 4) doubles of shared memory, free during reduce
 };
-constexpr size_t kSolveScratchBytes = (size_t)kNumDots * (kThreads / 4) * sizeof(double);
+
+// Sum 32 per-lane values across the warp for 32 different quantities at once: after the call
+// lane l holds the warp total of v[l] in v[0]. A butterfly that halves the number of live values
+// per stage: 31 shuffles instead of 32 x 5, in a fixed order.
+__device__ __forceinline__ void warp_transpose_sum(double (&v)[kNumDots], int lane)
+{
+    static_assert(kNumDots == 32, "one quantity per lane");
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const double send = upper ? v[i] : v[i + off];
+            const double keep = upper ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+}
 
 // Problem concept:
-//   double eval_partial(const double *x)        phase E, all threads; returns the CTA's partial f
-//   double grad_coord(int k, double xk, double &faug)   reduced gradient of coordinate k (xk = x[k])
+//   double eval_partial(const double *x)   phase E, all threads; returns a per-thread value whose
+//                                          sum over the CTA is the CTA's partial data term f
+//   double aug_term(int k, double xk, double &faug)   part of the gradient of coordinate k that
+//                                          depends only on x (xk = x[k]) and on data that is
+//                                          constant during the solve; adds its objective part to faug
+//   kBatch, data_issue(k, v), data_finish(k, v)   the part reduced over the group's phase-E
+//                                          partials: issue starts the first batch of loads,
+//                                          finish sums them (and any further batches)
 // Runs to completion; returns the number of evaluations (identical in all CTAs). status: 0 ok,
 // 1 line search failed (ExceptionWithIflag in the reference), 2 numeric trouble.
 // eval_cap: stop (unfinished, state kept in sm.st) once that many evaluations have been made in
 // total; resume: sm.st already holds the state of an interrupted solve. finished tells which.
+//
+// Latency notes (B200, cfg-2, measured with SQW_ADMM_PROFILE). A trip of the loop is
+// E | barrier | R | barrier | S | U | barrier, and every phase but E is a handful of dependent L2
+// round trips (~1 us each for lines another SM has just written). So
+//  * the per-coordinate operands of R and U (x, d, g_old, wa, S, Y of the CTA's slice) live in
+//    shared memory when the slice fits (ws.slice): global memory only receives the write-through
+//    copy the next launch resumes from, and R's only global loads are the group's partials;
+//  * U keeps its operands in registers from R;
+//  * the 32 scalar partials are reduced by a transposing butterfly (31 shuffles per warp).
+struct CoordRegs {
+    double x, d, go, wa, gaug, faug;
+    double s[kLbfgsM], y[kLbfgsM];
+};
+
 template <class Problem>
 __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier &gb,
                                  SolveSmem &sm, double eps, double xtol, int &status,
@@ -543,10 +606,31 @@ __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier 
     // coordinate slice of this CTA: whole 128-byte lines, so no line is shared between CTAs
     const int sl = ((n + G - 1) / G + 15) & ~15;
     const int k0 = min(n, cta * sl), k1 = min(n, k0 + sl);
+    const int kf = k0 + (int)threadIdx.x;  // this thread's first coordinate
+    const bool mine = kf < k1;
     LbState &st = sm.st;
     if (!resume) {
         for (int i = threadIdx.x; i < (int)(sizeof(LbState) / sizeof(int)); i += kThreads)
             reinterpret_cast<int *>(&st)[i] = 0;
+    }
+    // slice cache: thread t owns slot t of every vector (kSliceCap < kThreads: one coordinate each)
+    static_assert(kSliceCap <= kThreads, "one slice coordinate per thread");
+    const bool cached = ws.slice != nullptr && k1 - k0 <= kSliceCap;
+    double *const cx = ws.slice + threadIdx.x;             // + v * kSliceCap: vector v
+    double *const cd = cx + kSliceCap, *const cgo = cx + 2 * kSliceCap, *const cwa = cx + 3 * kSliceCap;
+    double *const cS = cx + 4 * kSliceCap, *const cY = cx + (4 + kLbfgsM) * kSliceCap;
+    if (cached && mine) {
+        *cx = __ldcg(ws.x + kf);
+        if (resume) {
+            *cd = ws.d[kf];
+            *cgo = ws.gold[kf];
+            *cwa = ws.wa[kf];
+#pragma unroll
+            for (int i = 0; i < kLbfgsM; ++i) {
+                cS[i * kSliceCap] = ws.S[(size_t)i * n + kf];
+                cY[i * kSliceCap] = ws.Y[(size_t)i * n + kf];
+            }
+        }
     }
     __syncthreads();
     // history slots to reduce against (excludes the slot being replaced) / slot y_new is written to
@@ -556,16 +640,63 @@ __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier 
     bool done = false;
     status = 0;
 
-    for (;;) {
+    // operands of coordinate k for phase R (and U): everything but the phase-E partials
+    auto load_coord = [&](int k, CoordRegs &c, bool from_cache) {
+        c.d = c.go = c.wa = 0.0;
+#pragma unroll
+        for (int i = 0; i < kLbfgsM; ++i)
+            c.s[i] = c.y[i] = 0.0;
+        if (from_cache) {
+            c.x = *cx;
+            if (!first) {
+                c.d = *cd;
+                c.go = *cgo;
+                c.wa = *cwa;
+#pragma unroll
+                for (int i = 0; i < kLbfgsM; ++i) {
+                    if ((valid >> i) & 1u) {
+                        c.s[i] = cS[i * kSliceCap];
+                        c.y[i] = cY[i * kSliceCap];
+                    }
+                }
+            }
+        } else {
+            c.x = __ldcg(ws.x + k);
+            if (!first) {
+                c.d = ws.d[k];
+                c.go = ws.gold[k];
+                c.wa = ws.wa[k];
+#pragma unroll
+                for (int i = 0; i < kLbfgsM; ++i) {
+                    if ((valid >> i) & 1u) {
+                        c.s[i] = ws.S[(size_t)i * n + k];
+                        c.y[i] = ws.Y[(size_t)i * n + k];
+                    }
+                }
+            }
+        }
+        c.faug = 0.0;
+        c.gaug = prob.aug_term(k, c.x, c.faug);
+    };
+
+    for (int trip = 0;; ++trip) {
         // ---- phase E: data-term partials of this CTA at the trial point
-        long long tk0 = 0, tk1 = 0;
+        long long tk0 = 0, tk1 = 0, tk2 = 0;
         if (ws.prof && threadIdx.x == 0)
             tk0 = sqw_now_ns();
 #define SQW_PROF(slot)                                   \
     if (ws.prof && threadIdx.x == 0) {                   \
-        tk1 = sqw_now_ns();                                 \
+        tk1 = sqw_now_ns();                              \
         ws.prof[slot] += tk1 - tk0;                      \
+        if (trip == 0)                                   \
+            ws.prof[24 + slot] += tk1 - tk0;             \
         tk0 = tk1;                                       \
+    }
+#define SQW_PROF2(slot)                                  \
+    if (ws.prof && threadIdx.x == 0) {                   \
+        const long long t2 = sqw_now_ns();               \
+        ws.prof[16 + slot] += t2 - tk2;                  \
+        tk2 = t2;                                        \
     }
         const double fpart = prob.eval_partial(ws.x);
         SQW_PROF(0)
@@ -573,91 +704,88 @@ __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier 
         SQW_PROF(1)
 
         // ---- phase R: one pass over my coordinate slice produces the reduced gradient, y_new
-        // and every scalar partial (each thread owns 1-2 coordinates; all loads of a coordinate
-        // are issued together, then the 32 partials are reduced through shared memory)
+        // and every scalar partial
         double pd[kNumDots];
 #pragma unroll
         for (int i = 0; i < kNumDots; ++i)
             pd[i] = 0.0;
         double *ynew = ws.Y + (size_t)point * n;
-        // one coordinate per trip (a slice is rarely longer than the CTA): every load of the
-        // coordinate is issued before any use
-        for (int k = k0 + threadIdx.x; k < k1; k += kThreads) {
-            const double xk = __ldcg(ws.x + k);
-            double dk = 0.0, go = 0.0, si[kLbfgsM], yi[kLbfgsM];
-            if (!first && !(prob.dbg() & 4)) {
-                dk = ws.d[k];
-                go = ws.gold[k];
-#pragma unroll
-                for (int i = 0; i < kLbfgsM; ++i) {
-                    si[i] = yi[i] = 0.0;
-                    if ((valid >> i) & 1u) {
-                        si[i] = ws.S[(size_t)i * n + k];
-                        yi[i] = ws.Y[(size_t)i * n + k];
-                    }
-                }
-            }
-            double faug = 0.0;
-            const double gk = prob.grad_coord(k, xk, faug);
-            ws.g[k] = gk;
-            pd[D_F] += faug;
+        auto reduce_coord = [&](int k, const CoordRegs &c, double gdata, double &gk_out,
+                                double &yn_out) {
+            const double gk = gdata + c.gaug;
+            pd[D_F] += c.faug;
             pd[D_GG] += gk * gk;
-            pd[D_XX] += xk * xk;
+            pd[D_XX] += c.x * c.x;
+            double yn = 0.0;
             if (!first) {
-                const double yn = gk - go;
+                yn = gk - c.go;
                 ynew[k] = yn;
-                pd[D_GD] += gk * dk;
+                pd[D_GD] += gk * c.d;
                 pd[D_GYN] += gk * yn;
                 pd[D_YNYN] += yn * yn;
-                pd[D_DYN] += dk * yn;
+                pd[D_DYN] += c.d * yn;
 #pragma unroll
                 for (int i = 0; i < kLbfgsM; ++i) {
                     if ((valid >> i) & 1u) {
-                        pd[D_GS + i] += gk * si[i];
-                        pd[D_GY + i] += gk * yi[i];
-                        pd[D_YNS + i] += yn * si[i];
-                        pd[D_YNY + i] += yn * yi[i];
-                        pd[D_DY + i] += dk * yi[i];
+                        pd[D_GS + i] += gk * c.s[i];
+                        pd[D_GY + i] += gk * c.y[i];
+                        pd[D_YNS + i] += yn * c.s[i];
+                        pd[D_YNY + i] += yn * c.y[i];
+                        pd[D_DY + i] += c.d * c.y[i];
                     }
                 }
             }
+            gk_out = gk;
+            yn_out = yn;
+        };
+        // the loads of the partials are issued first, the coordinate's other operands behind them
+        CoordRegs c0;
+        double g0 = 0.0, yn0 = 0.0;
+        tk2 = tk0;
+        if (mine) {
+            double v[Problem::kBatch];
+            prob.data_issue(kf, v);
+            load_coord(kf, c0, cached);
+            reduce_coord(kf, c0, prob.data_finish(kf, v), g0, yn0);
+            if (!cached)
+                ws.g[kf] = g0;
         }
-        if (threadIdx.x == 0)
-            pd[D_F] += fpart;
-        {
-            double *scr = sm.scratch;
-            __syncthreads();  // the evaluator is done with the shared region the scratch aliases
-#pragma unroll
-            for (int i = 0; i < kNumDots; ++i) {
-                double v = pd[i] + __shfl_xor_sync(0xffffffffu, pd[i], 1);
-                v += __shfl_xor_sync(0xffffffffu, v, 2);
-                if ((lane & 3) == 0)
-                    scr[i * (kThreads / 4) + (threadIdx.x >> 2)] = v;
-            }
-            __syncthreads();
-            for (int id = warp; id < kNumDots; id += kWarps) {
-                double acc = 0.0;
-#pragma unroll
-                for (int j = 0; j < (kThreads / 4 + 31) / 32; ++j)
-                    if (j * 32 + lane < kThreads / 4)
-                        acc += scr[id * (kThreads / 4) + j * 32 + lane];
-                acc = warp_sum(acc);
-                if (lane == 0)
-                    __stcg(ws.spart + (size_t)cta * kNumDots + id, acc);
-            }
+        for (int k = kf + kThreads; k < k1; k += kThreads) {  // (never with the slice cache)
+            CoordRegs c;
+            double v[Problem::kBatch], gk, yn;
+            prob.data_issue(k, v);
+            load_coord(k, c, false);
+            reduce_coord(k, c, prob.data_finish(k, v), gk, yn);
+            ws.g[k] = gk;
         }
+        pd[D_F] += fpart;
+        SQW_PROF2(0)
+        warp_transpose_sum(pd, lane);
+        sm.wred[warp][lane] = pd[0];
+        SQW_PROF2(1)
+        __syncthreads();
+        SQW_PROF2(2)
+        if (warp == 0) {
+            double acc = 0.0;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w)
+                acc += sm.wred[w][lane];
+            __stcg(ws.spart + (size_t)cta * kNumDots + lane, acc);
+        }
+        SQW_PROF2(3)
         SQW_PROF(2)
         gb.sync();
         SQW_PROF(3)
+        tk2 = tk0;
 
         // ---- phase S: every CTA reduces the G partials identically and takes the same decision
         if (warp == 0) {
             double s = 0.0;
-            for (int c0 = 0; c0 < G; c0 += 32) {
+            for (int cb = 0; cb < G; cb += 32) {
                 double v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                    v[j] = (c0 + j < G) ? __ldcg(ws.spart + (size_t)(c0 + j) * kNumDots + lane) : 0.0;
+                    v[j] = (cb + j < G) ? __ldcg(ws.spart + (size_t)(cb + j) * kNumDots + lane) : 0.0;
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
                     s += v[j];
@@ -665,12 +793,14 @@ __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier 
             sm.dots[lane] = s;
             const int bad = __any_sync(0xffffffffu, isnan(s) || isinf(s));
             __syncwarp();
+            SQW_PROF2(4)
             if (lane == 0) {
                 int fatal = bad;
                 if (!fatal)
                     lbfgs_scalar_step(st, sm.dots, eps, xtol, sm.dec, fatal, first);
                 sm.fatal = fatal;
             }
+            SQW_PROF2(5)
         }
         __syncthreads();
         SQW_PROF(4)
@@ -686,10 +816,47 @@ __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier 
             break;
         }
         if (dec.action == ACT_LINESEARCH) {
-            for (int k = k0 + threadIdx.x; k < k1; k += kThreads)
+            if (mine) {
+                const double xn = c0.wa + dec.stp * c0.d;
+                ws.x[kf] = xn;
+                if (cached)
+                    *cx = xn;
+            }
+            for (int k = kf + kThreads; k < k1; k += kThreads)
                 ws.x[k] = ws.wa[k] + dec.stp * ws.d[k];
         } else {  // ACT_NEWDIR
-            for (int k = k0 + threadIdx.x; k < k1; k += kThreads) {
+            if (mine) {
+                // operands still in registers from phase R; the pair being stored at dec.slot is
+                // (stp_accept * d, y_new)
+                const double snew = dec.stp_accept * c0.d;
+                if (dec.slot >= 0) {
+                    ws.S[(size_t)dec.slot * n + kf] = snew;
+                    if (cached) {
+                        cS[dec.slot * kSliceCap] = snew;
+                        cY[dec.slot * kSliceCap] = yn0;
+                    }
+                }
+                double dn = dec.cg * g0;
+#pragma unroll
+                for (int i = 0; i < kLbfgsM; ++i)
+                    if ((dec.valid_mask >> i) & 1u) {
+                        const double si = (i == dec.slot) ? snew : c0.s[i];
+                        const double yi = (i == dec.slot) ? yn0 : c0.y[i];
+                        dn += dec.cs[i] * si + dec.cy[i] * yi;
+                    }
+                const double xn = c0.x + dec.stp * dn;
+                ws.gold[kf] = g0;
+                ws.wa[kf] = c0.x;
+                ws.d[kf] = dn;
+                ws.x[kf] = xn;
+                if (cached) {
+                    *cgo = g0;
+                    *cwa = c0.x;
+                    *cd = dn;
+                    *cx = xn;
+                }
+            }
+            for (int k = kf + kThreads; k < k1; k += kThreads) {
                 const double gk = ws.g[k];
                 if (dec.slot >= 0)
                     ws.S[(size_t)dec.slot * n + k] = dec.stp_accept * ws.d[k];
@@ -711,12 +878,16 @@ __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier 
         SQW_PROF(5)
         gb.sync();
         SQW_PROF(6)
-        if (ws.prof && threadIdx.x == 0)
+        if (ws.prof && threadIdx.x == 0) {
             ws.prof[7] += 1;
+            if (trip == 0)
+                ws.prof[31] += 1;
+        }
         if (st.evals >= eval_cap)  // identical in every CTA; the trial point for the next
             break;                 // evaluation is already in place
     }
 #undef SQW_PROF
+#undef SQW_PROF2
     if (finished)
         *finished = done;
     int evals = 0;

@@ -18,6 +18,7 @@ constexpr int kLbfgsM = 5;        // L-BFGS history length (LOne.java:868)
 constexpr int kThreads = 352;     // threads per CTA of the x-update kernel: 8 DMMA + 2 softmax +
                                   // 1 producer warp; 65536 / 352 leaves 184 registers per thread
 constexpr int kWarps = kThreads / 32;
+constexpr int kProfSlots = 32;  // SQW_ADMM_PROFILE counters per CTA
 constexpr int kNumDots = 32;      // scalar partials exchanged per evaluation (see admm_solver.cuh)
 constexpr int kMaxEdgesPerLeaf = 32;
 constexpr int kMaxFanIn = 64;
@@ -69,7 +70,6 @@ struct AdmmDev {
     int upad;       // E * dimp
     int wstride;    // row stride of W in shared memory (bank-conflict free)
     int world;      // ranks
-    int dbg;        // timing experiments only (SQW_ADMM_DBG); 0 in production
     double ridge;   // lambda
 
     // ---- training data, block-major ----
