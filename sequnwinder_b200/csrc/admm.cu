@@ -260,6 +260,9 @@ static int prepare(sqw_admm *h)
     D.G = G;
     D.Gmax = G * D.T_local;
     D.nphase = kNumPhases;
+    // measured at cfg-2 (tools/gcap.sh): 64.5 us per evaluation round without a cap, 62.0 with 48,
+    // 63.6 with 36, 66.8 with 24; SQW_ADMM_GCAP is the tuning hook
+    D.gcap = getenv("SQW_ADMM_GCAP") ? std::max(1, atoi(getenv("SQW_ADMM_GCAP"))) : 48;
 
     int rc;
 #define TRY(x)            \

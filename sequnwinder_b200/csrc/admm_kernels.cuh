@@ -222,7 +222,8 @@ admm_xupdate_kernel(AdmmDev P, TileSmemLayout L, int phase, int eval_cap)
         s_blk = -1;
         s_G = 0;
         if (act > 0) {
-            const int G = (int)gridDim.x / act;
+            // (past gcap CTAs a group's reduction costs more than its shorter evaluation saves)
+            const int G = min((int)gridDim.x / act, P.gcap);
             const int grp = (int)blockIdx.x / G;
             if (grp < act) {
                 int seen = 0;

@@ -58,6 +58,7 @@ struct AdmmDev {
     int T_local;    // blocks owned by this rank
     int G;          // CTAs per block while every local block is active (= Gmax / T_local)
     int Gmax;       // CTAs of the x-update launch = slot stride of gpart / spart per block
+    int gcap;       // most CTAs a re-grouped block may get in a later phase
     int nphase;     // x-update launches per ADMM iteration (re-grouping points)
     int nb;         // rows per block = floor(N / T)
     int dim;        // numPredictors + 1
