@@ -178,6 +178,35 @@ int sqw_predict_dev(const double *d_par, int32_t dim, int32_t num_classes, const
                     int64_t n, int64_t numK, const int32_t *d_keep_idx, double *d_prob,
                     int32_t *d_argmax, void *stream);
 
+/* f-4. Hills scan: motifs/Discrim.java:328-444 (findHills :328-380, findSeqlets :382-444), the
+ * first consumer of the trained weights. Every window of length min_m..max_m (SeqUnwinderConfig
+ * minscanlen / maxscanlen, :429-430) of every sequence without 'N' is scored with the k-mer
+ * weights of one label (kmer_weights: numK doubles in count-matrix column order,
+ * Classifier.getWeights / SeqUnwinderConfig.getKmerBaseInd :198-204); scores are accumulated in
+ * the reference's order and are bit-identical to it. The per-sequence hill list follows the
+ * reference's iterator logic (:410-427): mode 0 = findSeqlets (an equal-scoring overlapping hill
+ * is kept), mode 1 = findHills (it is replaced); thresh = hillsthresh (:431).
+ *   hill_start / hill_len / hill_score : out, n x cap; entries [r*cap, r*cap + counts[r]) are the
+ *                                        hills of sequence r in list order (start is 0-based in
+ *                                        the sequence; findHills adds the region start, :355)
+ *   counts : out, n;  has_n : out, n (1 = sequence skipped, :337-338 / :389-390)
+ * The caller sorts by score (Collections.sort, stable, descending; :231-249) and cuts the
+ * substrings (:432-438). Returns SQW_ERR_BAD_BASE for a character outside ACGTN and
+ * SQW_ERR_UNSUPPORTED if a sequence yields more than cap hills. */
+int sqw_hills_scan(const char *bases, const int64_t *offsets, int64_t n, int kmin, int kmax,
+                   const double *kmer_weights, int min_m, int max_m, double thresh, int mode,
+                   int32_t cap, int32_t *hill_start, int32_t *hill_len, double *hill_score,
+                   int32_t *counts, uint8_t *has_n);
+
+/* Device-resident form: all pointers are device pointers, asynchronous on `stream`. max_len =
+ * longest sequence. d_status: one int32, OR-ed with 2 for a character outside ACGTN and with 4
+ * when a sequence overflowed cap (caller zeroes it and reads it back). */
+int sqw_hills_scan_dev(const uint8_t *d_bases, const int64_t *d_offsets, int64_t n, int64_t max_len,
+                       int kmin, int kmax, const double *d_kmer_weights, int min_m, int max_m,
+                       double thresh, int mode, int32_t cap, int32_t *d_hill_start,
+                       int32_t *d_hill_len, double *d_hill_score, int32_t *d_counts, uint8_t *d_has_n,
+                       int32_t *d_status, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Building blocks exposed for parity tests and micro-benchmarks (same kernels execute() uses).
  * ---------------------------------------------------------------------------------------- */

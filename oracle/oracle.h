@@ -34,6 +34,19 @@ int64_t orc_num_kmers(int kmin, int kmax);
 int orc_kmer_count(const char *bases, const int64_t *offsets, int64_t n, int kmin, int kmax,
                    int32_t *counts, uint8_t *has_n);
 
+/* ---- hills scan: motifs/Discrim.java:328-444 (findHills / findSeqlets) ---- */
+
+/* For every sequence without 'N': every window of length min_m..max_m is scored with the k-mer
+ * weights (kmer_weights: numK doubles in count-matrix column order) and the per-sequence list of
+ * non-overlapping "hills" is built with the reference's iterator logic. mode 0 = findSeqlets
+ * (ties keep both hills), 1 = findHills (ties replace). Hills of sequence r, in list order:
+ * hill_start/len/score[r*cap + 0 .. counts[r]). Returns 0; -1 on a character outside ACGTN;
+ * -4 if a sequence produced more than cap hills. */
+int orc_hills_scan(const char *bases, const int64_t *offsets, int64_t n, int kmin, int kmax,
+                   const double *kmer_weights, int min_m, int max_m, double thresh, int mode,
+                   int32_t cap, int32_t *hill_start, int32_t *hill_len, double *hill_score,
+                   int32_t *counts, uint8_t *has_n);
+
 /* ---- class structure: framework/Classifier.java:633-736 (ClassRelationStructure) ---- */
 typedef struct {
     int32_t num_nodes;          /* allNodes.size() */

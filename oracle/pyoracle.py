@@ -130,6 +130,37 @@ def kmer_count(bases: np.ndarray, offsets: np.ndarray, kmin: int, kmax: int):
     return counts, has_n
 
 
+def hills_scan(bases: np.ndarray, offsets: np.ndarray, kmin: int, kmax: int, weights: np.ndarray,
+               min_m: int, max_m: int, thresh: float, mode: int = 0, cap: int = 64):
+    """Oracle for Discrim.findSeqlets (mode 0) / findHills (mode 1): returns
+    (start[n, cap], length[n, cap], score[n, cap], counts[n], has_n[n])."""
+    n = len(offsets) - 1
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    weights = np.ascontiguousarray(weights, dtype=np.float64)
+    assert weights.size == num_kmers(kmin, kmax)
+    start = np.zeros((n, cap), dtype=np.int32)
+    length = np.zeros((n, cap), dtype=np.int32)
+    score = np.zeros((n, cap), dtype=np.float64)
+    counts = np.zeros(n, dtype=np.int32)
+    has_n = np.zeros(n, dtype=np.uint8)
+    buf = bases if bases.size else np.zeros(1, dtype=np.uint8)
+    L = lib()
+    L.orc_hills_scan.restype = C.c_int
+    L.orc_hills_scan.argtypes = [C.c_char_p, _i64p, C.c_int64, C.c_int, C.c_int, _f64p, C.c_int, C.c_int,
+                                 C.c_double, C.c_int, C.c_int32, _i32p, _i32p, _f64p, _i32p, _u8p]
+    rc = L.orc_hills_scan(buf.ctypes.data_as(C.c_char_p), _p(offsets, _i64p), n, kmin, kmax,
+                          _p(weights, _f64p), min_m, max_m, float(thresh), mode, cap, _p(start, _i32p),
+                          _p(length, _i32p), _p(score, _f64p), _p(counts, _i32p), _p(has_n, _u8p))
+    if rc == -1:
+        raise ValueError("Nonstandard nucleotide character encountered")
+    if rc == -4:
+        raise OverflowError("more hills in a sequence than cap")
+    if rc != 0:
+        raise ValueError(f"orc_hills_scan failed: {rc}")
+    return start, length, score, counts, has_n
+
+
 @dataclass
 class StructureArrays:
     """CSR form of a ClassRelationStructure, entries in design-file order."""

@@ -60,6 +60,12 @@ SYMBOLS = {
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sqw_predict_dev": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int64,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sqw_hills_scan": (C.c_int, [C.c_void_p, i64p, C.c_int64, C.c_int, C.c_int, f64p, C.c_int, C.c_int,
+                                 C.c_double, C.c_int, C.c_int32, i32p, i32p, f64p, i32p, u8p]),
+    "sqw_hills_scan_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int32,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]),
     "sqw_admm_eval": (C.c_int, [C.c_void_p, f64p, f64p, C.c_double, f64p, f64p]),
     "sqw_lbfgs_rosenbrock": (C.c_int, [C.c_int32, f64p, C.c_double, i32p, i32p, i32p]),
 }

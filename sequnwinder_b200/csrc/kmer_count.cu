@@ -18,6 +18,7 @@
 // Rows containing 'N' are flagged and written as zeros (the Java caller omits them,
 // MakeArff.java:354-355); any other character raises the status bit (seq2int would throw).
 #include "common.cuh"
+#include "kmer_pack.cuh"
 
 #include <algorithm>
 #include <vector>
@@ -36,49 +37,6 @@ struct KmerParams {
     int rows_per_block;
     int seq_words;  // 64-bit words reserved per sequence (incl. one pad word)
 };
-
-enum : int { kFlagN = 1, kFlagBad = 2 };
-
-__device__ __forceinline__ unsigned long long rev2_64(unsigned long long v)
-{
-    // reverse the order of the 32 two-bit groups of v
-    v = __brevll(v);
-    return ((v >> 1) & 0x5555555555555555ull) | ((v & 0x5555555555555555ull) << 1);
-}
-
-// Pack one sequence into MSB-first 2-bit words; returns flags seen by this thread's warp loop.
-__device__ __forceinline__ void pack_sequence(const uint8_t *__restrict__ seq, int64_t len,
-                                              unsigned long long *__restrict__ words, int t,
-                                              int tpr, int *flag_slot)
-{
-    const int lane = t & 31;
-    const int wg = t >> 5;
-    const int nwarps = tpr >> 5;
-    const int64_t nchunks = (len + 31) >> 5;
-    int flags = 0;
-    for (int64_t c = wg; c < nchunks; c += nwarps) {
-        const int64_t pos = (c << 5) + lane;
-        unsigned ch = (pos < len) ? (unsigned)seq[pos] : (unsigned)'A';
-        const unsigned up = ch & 0xDFu;
-        unsigned code = (up >> 1) & 3u;  // A0 C1 G3 T2
-        code ^= (code >> 1);             // A0 C1 G2 T3
-        const bool ok = (up == 'A') | (up == 'C') | (up == 'G') | (up == 'T');
-        if (!ok) {
-            flags |= (up == 'N') ? kFlagN : kFlagBad;
-            code = 0;
-        }
-        const unsigned sh = 30u - 2u * (unsigned)(lane & 15);
-        const unsigned hi = __reduce_or_sync(0xffffffffu, lane < 16 ? code << sh : 0u);
-        const unsigned lo = __reduce_or_sync(0xffffffffu, lane >= 16 ? code << sh : 0u);
-        if (lane == 0)
-            words[c] = ((unsigned long long)hi << 32) | (unsigned long long)lo;
-    }
-    if (t == 0)
-        words[nchunks] = 0ull;  // pad word read by the funnel shift of the last windows
-    flags = __reduce_or_sync(0xffffffffu, flags);
-    if (lane == 0 && flags)
-        atomicOr(flag_slot, flags);
-}
 
 // One window position: forward code = top 2k bits of `comb`, reverse-complement code = low 2k
 // bits of rev2_64(~comb). Target is either shared (ATOMS) or global (RED) memory.

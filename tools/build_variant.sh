@@ -8,5 +8,5 @@ mkdir -p ../_ab _obj
 nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xptxas -v "$@" \
     -c admm.cu -o _obj/admm_$name.o 2> _obj/admm_$name.ptxas.log
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../_ab/lib_$name.so _obj/admm_$name.o _obj/common.o \
-    _obj/kmer_count.o _obj/prepare_predict.o -ldl
+    _obj/kmer_count.o _obj/prepare_predict.o _obj/hills_scan.o -ldl
 grep -A3 "admm_xupdate_kernelILi1ELi5" _obj/admm_$name.ptxas.log | grep -E "spill"
