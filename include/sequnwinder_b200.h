@@ -111,6 +111,14 @@ int sqw_admm_set_structure(sqw_admm *h, int32_t num_nodes, int32_t num_layers,
 int sqw_admm_set_params(sqw_admm *h, double ridge, double pho, int32_t num_threads,
                         int32_t admm_max_itr, int32_t nodes_max_itr, int32_t debug);
 
+/* Regularisation sweep (BASELINE config 5: --r in {0.1 .. 100} on one training matrix; the
+ * reference would start a new JVM run per value, SeqUnwinderConfig.java:389 takes a scalar):
+ * changes lambda on a handle whose problem is already uploaded, so that successive
+ * sqw_admm_execute calls re-use the resident training matrix and workspace. Each execute starts
+ * from the x / sm_x it is given with fresh z, u, rho (a new LOne per run, LOne.java:80-85), so a
+ * sweep returns exactly what independent runs return. */
+int sqw_admm_set_ridge(sqw_admm *h, double ridge);
+
 /* Multi-GPU (one process per GPU): blocks t with t % world == rank live on this rank; the
  * consensus sums (LOne.java:395-417) become one ncclAllReduce per ADMM iteration.
  * nccl_id is the 128-byte ncclUniqueId produced by sqw_nccl_unique_id on rank 0 and

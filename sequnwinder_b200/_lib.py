@@ -48,6 +48,7 @@ SYMBOLS = {
                                          i32p, i32p, i32p, i32p]),
     "sqw_admm_set_params": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int32, C.c_int32,
                                       C.c_int32, C.c_int32]),
+    "sqw_admm_set_ridge": (C.c_int, [C.c_void_p, C.c_double]),
     "sqw_nccl_unique_id": (C.c_int, [u8p]),
     "sqw_admm_set_comm": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, u8p]),
     "sqw_admm_execute": (C.c_int, [C.c_void_p, f64p, f64p]),

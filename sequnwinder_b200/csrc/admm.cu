@@ -488,6 +488,19 @@ int sqw_admm_set_params(sqw_admm *h, double ridge, double pho, int32_t num_threa
     return SQW_OK;
 }
 
+int sqw_admm_set_ridge(sqw_admm *h, double ridge)
+{
+    if (!h)
+        return set_error(SQW_ERR_INVALID_ARG, "null handle");
+    if (!h->have_params)
+        return set_error(SQW_ERR_STATE, "set_params first");
+    if (!(ridge >= 0.0))
+        return set_error(SQW_ERR_INVALID_ARG, "ridge must be >= 0 (got %g)", ridge);
+    h->ridge = ridge;
+    h->dev.ridge = ridge;  // the training matrix and the workspace stay resident
+    return SQW_OK;
+}
+
 int sqw_admm_set_structure(sqw_admm *h, int32_t num_nodes, int32_t num_layers,
                            const int32_t *node_index, const int32_t *is_leaf, const int32_t *layer,
                            const int32_t *parent_ptr, const int32_t *parent_idx,

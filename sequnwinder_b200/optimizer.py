@@ -241,6 +241,30 @@ class LOneCuda(Optimizer):
         self.log = AdmmLog(lo[:r], li[:r], lp[:r], lf[:r], lpr[:r], ld[:r], ln[:r],
                            [int(v) for v in ai[:stats.outer_iters]])
 
+    def sweep(self, ridges):
+        """Regularisation sweep on one uploaded problem (BASELINE config 5): for every lambda in
+        ``ridges`` run execute() from the x / sm_x this optimizer was constructed with, keeping
+        the training matrix resident on the device. Returns [(x, sm_x, stats, log)] in order;
+        each entry equals what a fresh LOneCuda with setRidge(lambda) returns."""
+        lib = _lib.load()
+        x0, smx0 = np.array(self.x, dtype=np.float64), np.array(self.sm_x, dtype=np.float64)
+        keep, self._resident = self._resident, True
+        out = []
+        try:
+            for lam in ridges:
+                np.copyto(self.x, x0.reshape(self.x.shape))
+                np.copyto(self.sm_x, smx0.reshape(self.sm_x.shape))
+                self.setRidge(float(lam))
+                if self._handle is not None:
+                    _lib.check(lib.sqw_admm_set_ridge(self._handle, float(lam)))
+                self.execute()
+                out.append((np.array(self.x), np.array(self.sm_x), self.stats, self.log))
+        finally:
+            self._resident = keep
+            if not keep:
+                self.close()
+        return out
+
     def getX(self): return self.x
     def getsmX(self): return self.sm_x
 

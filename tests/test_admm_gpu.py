@@ -172,6 +172,35 @@ def test_full_size_cfg1_properties(oracle):
     assert lo.log.nfev.min() >= 2
 
 
+def test_ridge_sweep_equals_independent_runs(oracle):
+    """BASELINE config 5 (regularisation sweep on one matrix): sweep() re-uses the resident
+    training matrix; every entry must equal a fresh optimizer's run bit for bit, and the oracle's
+    run at that lambda within the stated tolerance."""
+    p = make_problem("cfg1", 500, max_features=60)
+    T, A, S = 5, 30, 2
+    ridges = [0.1, 1.0, 10.0, 100.0]
+    lo = opt.LOneCuda(p.x0.copy(), p.smx0.copy(), p.data)
+    lo.setADMMmaxItrs(A); lo.setBGFSmaxItrs(-1); lo.setSeqUnwinderMaxIts(S)
+    lo.setClassStructure(p.crs); lo.setClsMembership(p.cls); lo.setInstanceWeights(p.weights)
+    lo.setNumClasses(p.num_classes); lo.setNumPredictors(p.data.shape[1] - 1)
+    lo.setPho(1.7); lo.set_numThreads(T); lo.initUandZ()
+    res = lo.sweep(ridges)
+    assert lo._handle is None                      # not resident: the handle is released
+    norms = []
+    for lam, (x, smx, stats, log) in zip(ridges, res):
+        one = run_gpu(p, T, A, S, ridge=lam)
+        assert np.array_equal(x, one.getX()) and np.array_equal(smx, one.getsmX())
+        assert log.admm_iters == one.log.admm_iters
+        xo, smo, tr = oracle.lone_execute(p.x0, p.smx0, p.data, p.cls, p.weights, p.st, p.num_classes,
+                                          ridge=lam, num_threads=T, admm_max_itr=A, nodes_max_itr=S,
+                                          host_threads=8)
+        assert log.admm_iters == tr.admm_iters
+        assert np.abs(x - xo).max() <= REL_TOL * np.abs(xo).max()
+        assert np.abs(smx - smo).max() <= REL_TOL * np.abs(smo).max()
+        norms.append(np.abs(smx).sum())
+    assert norms[0] > norms[-1]                    # stronger L1 penalty, smaller label weights
+
+
 def test_errors_are_reported():
     p = make_problem("cfg1", 100, max_features=8)
     lo = opt.LOneCuda(p.x0.copy(), p.smx0.copy(), p.data)
