@@ -416,7 +416,7 @@ static int enqueue_iteration(sqw_admm *h, int slot)
     admm_consensus_kernel<<<D.E, kThreads, 0, h->stream>>>(D);  // block_sum() needs kThreads
     if ((rc = nccl_allreduce(h, D.sum2, (size_t)D.E)) != SQW_OK)
         return rc;
-    admm_decide_kernel<<<1, 32, 0, h->stream>>>(D);
+    admm_decide_kernel<<<1, kDecideThreads, 0, h->stream>>>(D);
     SQW_CUDA_CHECK(cudaMemcpyAsync(&h->h_ring[slot], D.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost,
                                    h->stream));
     SQW_CUDA_CHECK(cudaEventRecord(h->ev_snap[slot], h->stream));
