@@ -390,6 +390,12 @@ def main():
             "value": v, "unit": UNIT, "cores": threads, "kind": "port", "host_cores": cores,
             "sample": f"first {its} ADMM iterations of outer iteration 1, full cfg2 matrix, "
                       f"T={T} blocks on {threads} pthreads ({s:.1f} s)"}
+        # the reference's default --threads 5 as well: same matrix, 5 blocks
+        v5, s5, its5, _ = cpu_oracle_sample(prep.data, prep.x0, prep.sm_x0, cls, w, crs, C, 5, 2,
+                                            min(5, cores))
+        line["cpu_baseline"]["threads5"] = {
+            "value": v5, "cores": min(5, cores),
+            "sample": f"first {its5} ADMM iterations, T=5 blocks on {min(5, cores)} pthreads ({s5:.1f} s)"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
