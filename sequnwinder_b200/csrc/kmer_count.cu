@@ -21,6 +21,9 @@
 #include "kmer_pack.cuh"
 
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <tuple>
 #include <vector>
 
 namespace sqw {
@@ -221,6 +224,33 @@ static int64_t num_kmers(int kmin, int kmax)
     return numK;
 }
 
+// cudaFuncSetAttribute + the occupancy query cost tens of microseconds of host time, as much as
+// the kernel itself at cfg-2: remember them per (kernel, shared-memory size) and device.
+template <typename Kernel>
+static int cached_occupancy(Kernel kernel, int which, int threads, size_t smem, int *per_sm)
+{
+    static std::mutex mu;
+    static std::map<std::tuple<int, int, size_t>, int> cache;
+    int dev = 0;
+    SQW_CUDA_CHECK(cudaGetDevice(&dev));
+    static std::map<std::pair<int, int>, size_t> attr_set;  // (device, kernel) -> size last set
+    std::lock_guard<std::mutex> lock(mu);
+    size_t &cur = attr_set[std::make_pair(dev, which)];
+    if (cur != smem) {  // the attribute is per function: re-set it when the size changes
+        SQW_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cur = smem;
+    }
+    const auto key = std::make_tuple(dev, which, smem);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        int v = 1;
+        SQW_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, threads, smem));
+        it = cache.emplace(key, std::max(v, 1)).first;
+    }
+    *per_sm = it->second;
+    return SQW_OK;
+}
+
 static int launch_kmer(const uint8_t *d_bases, const int64_t *d_offsets, int64_t n,
                        int64_t max_len, int kmin, int kmax, int32_t *d_counts, uint8_t *d_has_n,
                        int32_t *d_status, cudaStream_t stream)
@@ -262,14 +292,10 @@ static int launch_kmer(const uint8_t *d_bases, const int64_t *d_offsets, int64_t
             // one warp per row: warp-synchronous kernel, 8 rows in flight per CTA
             p.rows_per_block = 8;
             const size_t wsmem = 8 * (hist_bytes + seq_bytes) + 8 * sizeof(int) + 16;
-            SQW_CUDA_CHECK(cudaFuncSetAttribute(kmer_count_warp_kernel,
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                (int)wsmem));
             int per_sm_w = 1;
-            SQW_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                &per_sm_w, kmer_count_warp_kernel, threads, wsmem));
-            if (per_sm_w < 1)
-                per_sm_w = 1;
+            int rc = cached_occupancy(kmer_count_warp_kernel, 0, threads, wsmem, &per_sm_w);
+            if (rc != SQW_OK)
+                return rc;
             const int64_t nblk = (n + 7) / 8;
             const int gridw = (int)std::min<int64_t>(nblk, (int64_t)kNumSMs * per_sm_w);
             kmer_count_warp_kernel<<<gridw, threads, wsmem, stream>>>(p);
@@ -278,14 +304,10 @@ static int launch_kmer(const uint8_t *d_bases, const int64_t *d_offsets, int64_t
         }
         p.rows_per_block = R;
         const size_t smem = (size_t)R * (hist_bytes + seq_bytes) + (size_t)R * sizeof(int) + 16;
-        SQW_CUDA_CHECK(cudaFuncSetAttribute(kmer_count_smem_kernel,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)smem));
         int per_sm = 1;
-        SQW_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-            &per_sm, kmer_count_smem_kernel, threads, smem));
-        if (per_sm < 1)
-            per_sm = 1;
+        int rc = cached_occupancy(kmer_count_smem_kernel, 1, threads, smem, &per_sm);
+        if (rc != SQW_OK)
+            return rc;
         const int64_t nbatches = (n + R - 1) / R;
         const int grid = (int)std::min<int64_t>(nbatches, (int64_t)kNumSMs * per_sm);
         kmer_count_smem_kernel<<<grid, threads, smem, stream>>>(p);
