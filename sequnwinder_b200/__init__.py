@@ -6,6 +6,7 @@ interfaces. There is no CPU fallback.
 """
 from .kmer import KmerCounter, kmer_names, num_kmers, pack_sequences  # noqa: F401
 from .structure import ClassRelationStructure, make_design  # noqa: F401
+from .hills import HillsScanner  # noqa: F401
 
 __all__ = ["KmerCounter", "kmer_names", "num_kmers", "pack_sequences",
-           "ClassRelationStructure", "make_design"]
+           "ClassRelationStructure", "make_design", "HillsScanner"]

@@ -46,6 +46,15 @@ def block_rows(n_rows: int, T: int, t: int):
     return [t + T * s for s in range(nb)]
 
 
+def local_ridges(ridges, rank: int, world: int):
+    """Regularisation sweep (BASELINE config 5) on several GPUs: the solves are independent, so
+    they are dealt out as replicas, no collective: value i runs on rank ``i % world``. Returns
+    [(index, lambda)] for ``rank``; every rank then calls ``LOneCuda.sweep`` on its own values."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("invalid rank/world")
+    return [(i, float(v)) for i, v in enumerate(ridges) if i % world == rank]
+
+
 def broadcast_bytes(payload: Optional[bytes], nbytes: int, src: int = 0) -> bytes:
     """Broadcast a fixed-size byte string over the default torch.distributed group (any backend)."""
     import torch

@@ -88,6 +88,20 @@ def test_world_size_two_gloo():
     assert all(v < 1e-13 for v in out.values()), dict(out)
 
 
+def test_sweep_values_are_dealt_out_as_replicas():
+    from sequnwinder_b200 import parallel
+    ridges = [0.1 * 10 ** (i / 5) for i in range(16)]
+    seen = []
+    for world in (1, 2, 8):
+        parts = [parallel.local_ridges(ridges, r, world) for r in range(world)]
+        flat = sorted(p for part in parts for p in part)
+        assert flat == list(enumerate(ridges))                  # every value exactly once
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+        seen.append(parts)
+    with pytest.raises(ValueError):
+        parallel.local_ridges(ridges, 2, 2)
+
+
 def test_local_blocks_errors():
     sys.path.insert(0, ROOT)
     from sequnwinder_b200 import parallel
