@@ -260,9 +260,13 @@ static int prepare(sqw_admm *h)
     D.G = G;
     D.Gmax = G * D.T_local;
     D.nphase = kNumPhases;
-    // measured at cfg-2 (tools/gcap.sh): 64.5 us per evaluation round without a cap, 62.0 with 48,
-    // 63.6 with 36, 66.8 with 24; SQW_ADMM_GCAP is the tuning hook
-    D.gcap = getenv("SQW_ADMM_GCAP") ? std::max(1, atoi(getenv("SQW_ADMM_GCAP"))) : 48;
+    // measured at cfg-2 (2 500 rows per block; tools/gcap.sh): 64.5 us per evaluation round
+    // without a cap, 62.0 with 48, 63.6 with 36, 66.8 with 24. A trip costs ~ rows/G of evaluation
+    // plus ~ G of partial-gradient exchange (both scale with C * dim), so the best G grows with
+    // the square root of the block's rows: 48 at 2 500 rows, no cap in effect for large blocks.
+    // SQW_ADMM_GCAP is the tuning hook.
+    const int gcap_auto = std::max(16, (int)(0.96 * std::sqrt((double)D.nb) + 0.5));
+    D.gcap = getenv("SQW_ADMM_GCAP") ? std::max(1, atoi(getenv("SQW_ADMM_GCAP"))) : gcap_auto;
 
     int rc;
 #define TRY(x)            \
