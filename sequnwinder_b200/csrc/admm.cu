@@ -96,6 +96,7 @@ struct sqw_admm {
 
     // params
     bool have_params = false, have_structure = false, have_problem = false, prepared = false;
+    bool l2_persist = false;  // this handle set the device's persisting-L2 carve-out
     double ridge = 10.0, pho = 1.7;
     int T = 5, admm_max_itr = 400, nodes_max_itr = 15, debug = 0;
 
@@ -323,16 +324,17 @@ static int prepare(sqw_admm *h)
     TRY(h->dalloc(&D.log_primal, cap));
     TRY(h->dalloc(&D.log_dual, cap));
 #undef TRY
-    // Keep as much of the training matrix as the part allows resident in L2 across evaluations:
-    // every evaluation re-reads the same X, and a plain cyclic sweep over a working set close to
-    // the L2 size thrashes (ncu: 23 % hit rate at cfg-2). A persisting access-policy window with
-    // hitRatio = persisting bytes / window bytes pins that fraction of the lines.
-    if (!getenv("SQW_ADMM_NO_L2_PERSIST")) {
+    // Optional (SQW_ADMM_L2_PERSIST_MB=<MB>): a persisting access-policy window over the training
+    // matrix, hitRatio = persisting bytes / window bytes. Every evaluation re-reads the same X and
+    // a cyclic sweep over a working set close to the L2 size thrashes (ncu: 23 % hit rate at
+    // cfg-2), but pinning part of it made no measurable difference to the x-update, and the
+    // carve-out is a device-wide setting that slows other kernels (the k-mer pass ran 4x slower
+    // next to a resident trainer), so it is off unless asked for.
+    if (const char *env = getenv("SQW_ADMM_L2_PERSIST_MB")) {
         const size_t x_bytes = (size_t)D.T_local * D.nb * D.dimp * sizeof(double);
-        size_t persist = (size_t)prop.persistingL2CacheMaxSize;
-        if (const char *env = getenv("SQW_ADMM_L2_PERSIST_MB"))
-            persist = std::min(persist, (size_t)atol(env) << 20);
+        size_t persist = std::min((size_t)prop.persistingL2CacheMaxSize, (size_t)atol(env) << 20);
         if (persist > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist) == cudaSuccess) {
+            h->l2_persist = true;
             cudaStreamAttrValue attr;
             memset(&attr, 0, sizeof attr);
             const size_t win = std::min(x_bytes, (size_t)prop.accessPolicyMaxWindowSize);
@@ -454,6 +456,10 @@ void sqw_admm_destroy(sqw_admm *h)
     cudaSetDevice(h->device);
     if (h->stream)
         cudaStreamSynchronize(h->stream);
+    if (h->l2_persist) {  // give the device-wide L2 carve-out back
+        cudaCtxResetPersistingL2Cache();
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+    }
     // the NCCL communicator is shared between handles and outlives them (see sqw_admm_set_comm)
     for (void *p : h->allocs)
         cudaFree(p);
