@@ -55,9 +55,25 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 }
 
 // 1-D bulk copy global -> shared, completion signalled on an mbarrier (TMA engine; SASS UBLKCP)
+#ifndef SQW_X_EVICT_FIRST
+#define SQW_X_EVICT_FIRST 1
+#endif
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes,
                                          unsigned long long *bar)
 {
+#if SQW_X_EVICT_FIRST
+    // the training matrix is streamed once per evaluation and never re-used from L2 (104 MB per
+    // pass at cfg-2): mark its lines evict-first so that the group's exchange buffers (partial
+    // gradients, scalars, trial point) are not pushed out to HBM between a write and its read
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+        : "memory");
+    return;
+#endif
     asm volatile(
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
             smem_u32(dst)),
