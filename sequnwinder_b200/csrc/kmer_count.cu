@@ -21,6 +21,7 @@
 #include "kmer_pack.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -178,6 +179,117 @@ __global__ void __launch_bounds__(256) kmer_count_warp_kernel(KmerParams p)
     }
 }
 
+// 32-bit variant of the warp-per-sequence kernel for kmax <= 16 (the API caps k at 15) with the k
+// range known at compile time (NK = kmax - kmin + 1 <= 5). Same results; what changes is the
+// instruction count and the exposed latency per row, which bounded the kernel above at the
+// k = 4..5 shape (ncu / CUDA events on B200: 4.2 TB/s of 6.56, ~750 warp instructions per row):
+//   * codes and the N / bad-character flags come from a 256-entry table in shared memory, the
+//     bytes of up to 8 chunks of 32 bases are loaded before the first one is used (one exposed
+//     global latency per row instead of one per chunk), the flags are reduced in registers;
+//   * the packed stream is kept as 32-bit words (16 bases each, first base most significant): a
+//     window of k <= 16 bases is two LDS.32 + one funnel shift, its reverse complement one BREV +
+//     pair swap, and every per-k step (shift, mask, min, bounds test, address) is 32-bit;
+//   * the histogram is re-zeroed unconditionally while the row is streamed out.
+template <int NK>
+__global__ void __launch_bounds__(256) kmer_count_warp32_kernel(KmerParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ unsigned char lut[256];
+    const int warps = blockDim.x >> 5;
+    const int g = threadIdx.x >> 5;
+    const int t = threadIdx.x & 31;
+    const int numK = (int)p.numK;
+    const int words32 = 2 * p.seq_words;  // 32-bit words reserved per sequence (>= 2 pad words)
+    int32_t *hist = reinterpret_cast<int32_t *>(smem) + (size_t)g * numK;
+    unsigned *words = reinterpret_cast<unsigned *>(smem + (size_t)warps * numK * sizeof(int32_t)) +
+                      (size_t)g * words32;
+    {
+        // table: bits 0-1 code (A0 C1 G2 T3, either case), bit 2 'N' / 'n', bit 3 anything else
+        const unsigned ch = threadIdx.x & 255u, up = ch & 0xDFu;
+        unsigned code = (up >> 1) & 3u;
+        code ^= (code >> 1);
+        const bool ok = (up == 'A') | (up == 'C') | (up == 'G') | (up == 'T');
+        lut[ch] = ok ? (unsigned char)code : (unsigned char)((up == 'N') ? 4u : 8u);
+    }
+    const int n4 = numK >> 2;
+    int4 *h4 = reinterpret_cast<int4 *>(hist);
+    for (int i = t; i < n4; i += 32)
+        h4[i] = make_int4(0, 0, 0, 0);
+    __syncthreads();
+    const int kmin = p.kmin;
+    // shift of the forward code / mask of the reverse-complement code / histogram offset per k
+    int fsh[NK], boff[NK];
+    unsigned msk[NK];
+#pragma unroll
+    for (int j = 0, b = 0; j < NK; ++j) {
+        const int k = kmin + j;
+        fsh[j] = 32 - 2 * k;
+        msk[j] = (k == 16) ? 0xffffffffu : ((1u << (2 * k)) - 1u);
+        boff[j] = b;
+        b += 1 << (2 * k);
+    }
+    const unsigned sh = 30u - 2u * (unsigned)(t & 15);
+    for (int64_t row = (int64_t)blockIdx.x * warps + g; row < p.n; row += (int64_t)gridDim.x * warps) {
+        const int64_t beg = p.offsets[row];
+        const int len = (int)(p.offsets[row + 1] - beg);
+        const uint8_t *seq = p.bases + beg;
+        const int nchunks = (len + 31) >> 5;
+        unsigned flags = 0;
+        for (int c0 = 0; c0 < nchunks; c0 += 8) {
+            unsigned ch[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int pos = ((c0 + u) << 5) + t;
+                ch[u] = (pos < len) ? (unsigned)__ldg(seq + pos) : (unsigned)'A';
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (c0 + u < nchunks) {  // warp uniform
+                    const unsigned e = lut[ch[u]];
+                    flags |= e;
+                    const unsigned v = (e & 3u) << sh;
+                    const unsigned hi = __reduce_or_sync(0xffffffffu, t < 16 ? v : 0u);
+                    const unsigned lo = __reduce_or_sync(0xffffffffu, t >= 16 ? v : 0u);
+                    if (t == 0)
+                        *reinterpret_cast<uint2 *>(words + 2 * (c0 + u)) = make_uint2(hi, lo);
+                }
+            }
+        }
+        if (t == 0)
+            *reinterpret_cast<uint2 *>(words + 2 * nchunks) = make_uint2(0u, 0u);  // pad for the funnel shift
+        const unsigned fl = __reduce_or_sync(0xffffffffu, flags) >> 2;  // bit 0: N, bit 1: bad
+        __syncwarp();
+        if (fl == 0) {
+            for (int i = t; i + kmin <= len; i += 32) {
+                const int w = i >> 4;
+                const unsigned cur = words[w], nxt = words[w + 1];
+                const unsigned comb = __funnelshift_l(nxt, cur, (i & 15) << 1);
+                unsigned rc = __brev(~comb);
+                rc = ((rc >> 1) & 0x55555555u) | ((rc & 0x55555555u) << 1);
+#pragma unroll
+                for (int j = 0; j < NK; ++j) {
+                    if (i + kmin + j <= len) {
+                        const unsigned f = comb >> fsh[j], r = rc & msk[j];
+                        atomicAdd(hist + boff[j] + (int)min(f, r), 1);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        int4 *dst = reinterpret_cast<int4 *>(p.counts + row * p.numK);
+        for (int i = t; i < n4; i += 32) {
+            __stcs(dst + i, h4[i]);
+            h4[i] = make_int4(0, 0, 0, 0);
+        }
+        if (t == 0) {
+            p.has_n[row] = (fl & 1u) ? 1 : 0;
+            if ((fl & 2u) && !(fl & 1u))
+                atomicOr(p.status, 1);
+        }
+        __syncwarp();
+    }
+}
+
 // Fallback for histograms that do not fit in shared memory (numK*4 > ~200 KB, i.e. k >= 8):
 // the output is cleared with a memset and one warp per sequence issues global RED.ADDs.
 __global__ void __launch_bounds__(256) kmer_count_global_kernel(KmerParams p)
@@ -293,10 +405,33 @@ static int launch_kmer(const uint8_t *d_bases, const int64_t *d_offsets, int64_t
             p.rows_per_block = 8;
             const size_t wsmem = 8 * (hist_bytes + seq_bytes) + 8 * sizeof(int) + 16;
             int per_sm_w = 1;
+            const int64_t nblk = (n + 7) / 8;
+            const int nk = kmax - kmin + 1;
+            if (nk <= 5 && max_len < (1 << 30) && !getenv("SQW_KMER_WARP64")) {
+                // k range known at compile time, 32-bit stream (see kmer_count_warp32_kernel)
+#define SQW_LAUNCH_W32(NK)                                                                      \
+    case NK: {                                                                                  \
+        int rc = cached_occupancy(kmer_count_warp32_kernel<NK>, 10 + NK, threads, wsmem, &per_sm_w); \
+        if (rc != SQW_OK)                                                                       \
+            return rc;                                                                          \
+        const int gridw = (int)std::min<int64_t>(nblk, (int64_t)kNumSMs * per_sm_w);            \
+        kmer_count_warp32_kernel<NK><<<gridw, threads, wsmem, stream>>>(p);                     \
+        break;                                                                                  \
+    }
+                switch (nk) {
+                    SQW_LAUNCH_W32(1)
+                    SQW_LAUNCH_W32(2)
+                    SQW_LAUNCH_W32(3)
+                    SQW_LAUNCH_W32(4)
+                    SQW_LAUNCH_W32(5)
+                }
+#undef SQW_LAUNCH_W32
+                SQW_CUDA_CHECK(cudaGetLastError());
+                return SQW_OK;
+            }
             int rc = cached_occupancy(kmer_count_warp_kernel, 0, threads, wsmem, &per_sm_w);
             if (rc != SQW_OK)
                 return rc;
-            const int64_t nblk = (n + 7) / 8;
             const int gridw = (int)std::min<int64_t>(nblk, (int64_t)kNumSMs * per_sm_w);
             kmer_count_warp_kernel<<<gridw, threads, wsmem, stream>>>(p);
             SQW_CUDA_CHECK(cudaGetLastError());
