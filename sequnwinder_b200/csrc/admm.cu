@@ -963,8 +963,9 @@ int sqw_admm_execute(sqw_admm *h, double *x_inout, double *smx_inout)
         const char *names[7] = {"eval", "barrier1", "reduce", "barrier2", "decide", "update", "barrier3"};
         const char *en[8] = {"kernel_epilogue", "tilewait", "pass1", "rr_wait", "kernel_prologue", "pass2",
                              "free_arrive", "combine"};
-        const char *sn[6] = {"R:loads+gradient", "R:products+shuffles", "R:sync", "R:warp sums+store",
-                             "S:partials", "S:scalar step"};
+        const char *sn[8] = {"R:loads+gradient", "R:products+shuffles", "R:sync", "R:warp sums+store",
+                             "S:partials", "S:scalar step", "R:partials arrived (probe)",
+                             "R:own operands + augmented term (probe)"};
         for (int ph = 0; ph < kNumPhases; ++ph) {
             const long long *q = &pr[(size_t)ph * D.Gmax * kProfSlots];
             if (!q[7])
@@ -976,8 +977,9 @@ int sqw_admm_execute(sqw_admm *h, double *x_inout, double *smx_inout)
             for (int i = 0; i < 8; ++i)
                 fprintf(stderr, " %s %.0f", en[i], (double)q[8 + i] / q[7]);
             fprintf(stderr, "\n[sqw profile]    solver breakdown per eval (ns):");
-            for (int i = 0; i < 6; ++i)
-                fprintf(stderr, " %s %.0f", sn[i], (double)q[16 + i] / q[7]);
+            for (int i = 0; i < 8; ++i)
+                if (i < 6 || q[16 + i])
+                    fprintf(stderr, " %s %.0f", sn[i], (double)q[16 + i] / q[7]);
             fprintf(stderr, "\n");
             if (q[31]) {
                 fprintf(stderr, "[sqw profile]    first trip of a launch (%lld launches, ns):", q[31]);

@@ -360,6 +360,9 @@ __device__ __forceinline__ unsigned hist_mask(int point, int hist)
 #ifndef SQW_SCALAR_NOINLINE
 #define SQW_SCALAR_NOINLINE 0
 #endif
+#ifndef SQW_PROF_SPLIT
+#define SQW_PROF_SPLIT 0   // probe: time the partial-gradient loads and the augmented term apart
+#endif
 #if SQW_SCALAR_NOINLINE
 __device__ __noinline__ void lbfgs_scalar_step(
 #else
@@ -745,8 +748,21 @@ __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier 
         if (mine) {
             double v[Problem::kBatch];
             prob.data_issue(kf, v);
+#if SQW_PROF_SPLIT
+            // probe build: serialise the two groups of loads and stamp after each has arrived
+            const double dsum = prob.data_finish(kf, v);
+            if (dsum == 1.2345e300)
+                tk2 += 1;
+            SQW_PROF2(6)
+            load_coord(kf, c0, cached);
+            if (c0.gaug == 1.2345e300)
+                tk2 += 1;
+            SQW_PROF2(7)
+            reduce_coord(kf, c0, dsum, g0, yn0);
+#else
             load_coord(kf, c0, cached);
             reduce_coord(kf, c0, prob.data_finish(kf, v), g0, yn0);
+#endif
             if (!cached)
                 ws.g[kf] = g0;
         }
