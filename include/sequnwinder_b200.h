@@ -119,6 +119,15 @@ int sqw_admm_set_params(sqw_admm *h, double ridge, double pho, int32_t num_threa
  * sweep returns exactly what independent runs return. */
 int sqw_admm_set_ridge(sqw_admm *h, double ridge);
 
+/* Concurrent sweep: caps the CTAs of this handle's cooperative x-update launches (0 = every SM).
+ * Handles with budgets that add up to the SM count, each driven by its own host thread, solve
+ * independent problems (the lambda values of a sweep, the folds of a cross-validation) side by
+ * side on one GPU: a block's group of CTAs shrinks, and with it the share of a solver trip that is
+ * L2 exchange between CTAs. Call before sqw_admm_set_problem. The group size enters the
+ * summation order of the partial gradients, so results agree with a full-GPU run to rounding
+ * (1e-16 per evaluation), not bit for bit. No reference counterpart. */
+int sqw_admm_set_cta_budget(sqw_admm *h, int32_t max_ctas);
+
 /* Multi-GPU (one process per GPU): blocks t with t % world == rank live on this rank; the
  * consensus sums (LOne.java:395-417) become one ncclAllReduce per ADMM iteration.
  * nccl_id is the 128-byte ncclUniqueId produced by sqw_nccl_unique_id on rank 0 and

@@ -17,6 +17,7 @@ SQW_OK = 0
 SQW_ERR_INVALID_ARG = -1
 SQW_ERR_NO_DEVICE = -2
 SQW_ERR_CUDA = -3
+B200_SMS = 148   # 2 dies x 74 SMs (csrc/common.cuh kNumSMs)
 SQW_ERR_BAD_BASE = -4
 SQW_ERR_UNSUPPORTED = -5
 SQW_ERR_NUMERIC = -6
@@ -49,6 +50,7 @@ SYMBOLS = {
     "sqw_admm_set_params": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int32, C.c_int32,
                                       C.c_int32, C.c_int32]),
     "sqw_admm_set_ridge": (C.c_int, [C.c_void_p, C.c_double]),
+    "sqw_admm_set_cta_budget": (C.c_int, [C.c_void_p, C.c_int32]),
     "sqw_nccl_unique_id": (C.c_int, [u8p]),
     "sqw_admm_set_comm": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, u8p]),
     "sqw_admm_execute": (C.c_int, [C.c_void_p, f64p, f64p]),

