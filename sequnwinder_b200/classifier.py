@@ -114,6 +114,7 @@ class Classifier:
         self.prep: Optional[Prepared] = None
         self.optimizer: Optional[LOneCuda] = None
         self.comm = None   # (rank, world, nccl_id) for multi-GPU runs
+        self.cta_budget = 0  # > 0: share of the GPU when several classifiers train side by side
 
     def buildClassifier(self, counts: np.ndarray, cls: np.ndarray, weights: np.ndarray,
                         num_classes: int):
@@ -136,6 +137,8 @@ class Classifier:
         opt.setDebugMode(self.sm_Debug)                     # :443
         if self.comm is not None:
             opt.setComm(*self.comm)
+        if self.cta_budget:
+            opt.setCtaBudget(self.cta_budget)
         opt.execute()                                       # :444
         x, sm_x = opt.getX(), opt.getsmX()                  # :447-448
         dim = prep.data.shape[1]
@@ -161,6 +164,90 @@ class Classifier:
             v[self.prep.keep] = self.sm_Par[1:, idx]
             out[name] = v
         return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Cross-validation (SeqUnwinder.java:41: weka Evaluation.crossValidateModel, "--x" folds): the
+# model on all sites plus one model per fold, each through Classifier.buildClassifier exactly as
+# Weka's loop does (train on the complement of the fold, predict the fold, pool the hits).
+@dataclass
+class CVResult:
+    accuracy: float              # pooled over the test folds (Evaluation.pctCorrect() / 100)
+    fold_accuracy: List[float]
+    predictions: np.ndarray      # arg-max class of every site that lies in a fold, else -1
+    full_model: "Classifier"
+    fold_models: List["Classifier"]
+
+
+def stratified_folds(cls: np.ndarray, num_folds: int, seed: int = 1) -> List[np.ndarray]:
+    """Deterministic stratified test-fold index lists: a seeded shuffle, then the sites of every
+    class dealt round-robin. These are NOT Weka's folds (Instances.randomize / stratify with
+    seed 1; Weka is not available here): a caller that needs Weka's exact folds
+    passes its own index lists to cross_validate."""
+    cls = np.asarray(cls)
+    rng = np.random.default_rng(seed)
+    order = rng.permutation(cls.size)
+    folds: List[List[int]] = [[] for _ in range(num_folds)]
+    nxt = 0
+    for c in np.unique(cls):
+        for i in order[cls[order] == c]:
+            folds[nxt % num_folds].append(int(i))
+            nxt += 1
+    return [np.sort(np.asarray(f, dtype=np.int64)) for f in folds]
+
+
+def cross_validate(structure: ClassRelationStructure, counts: np.ndarray, cls: np.ndarray,
+                   weights: np.ndarray, num_classes: int, folds: List[np.ndarray], slots: int = 1,
+                   **classifier_options) -> CVResult:
+    """1 + len(folds) trainings. ``slots`` > 1 runs them side by side on one GPU, each on
+    148 // slots CTAs (LOneCuda.setCtaBudget; DESIGN.md 2.5): the trainings are independent, so this
+    is the job-level batching the reference's one-JVM-thread loop cannot do."""
+    import queue
+    import threading
+
+    counts, cls, weights = np.asarray(counts), np.asarray(cls), np.asarray(weights)
+    n = counts.shape[0]
+    slots = max(1, min(int(slots), 1 + len(folds)))
+    budget = 0 if slots == 1 else 148 // slots
+    tasks: "queue.SimpleQueue" = queue.SimpleQueue()
+    tasks.put((-1, np.arange(n)))
+    for f, test in enumerate(folds):
+        train = np.setdiff1d(np.arange(n), np.asarray(test), assume_unique=False)
+        tasks.put((f, train))
+    models: Dict[int, Classifier] = {}
+    errors: list = []
+
+    def worker():
+        try:
+            while not errors:
+                try:
+                    f, rows = tasks.get_nowait()
+                except queue.Empty:
+                    return
+                clf = Classifier(structure, **classifier_options)
+                clf.cta_budget = budget
+                clf.buildClassifier(counts[rows], cls[rows], weights[rows], num_classes)
+                models[f] = clf
+        except Exception as exc:  # surfaced to the caller below
+            errors.append(exc)
+
+    threads = [threading.Thread(target=worker) for _ in range(slots)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    pred = np.full(n, -1, dtype=np.int64)
+    fold_acc = []
+    for f, test in enumerate(folds):
+        test = np.asarray(test)
+        pf = models[f].distributionForInstances(counts[test]).argmax(axis=1)
+        pred[test] = pf
+        fold_acc.append(float((pf == cls[test]).mean()) if test.size else float("nan"))
+    seen = pred >= 0
+    acc = float((pred[seen] == cls[seen]).mean()) if seen.any() else float("nan")
+    return CVResult(acc, fold_acc, pred, models[-1], [models[f] for f in range(len(folds))])
 
 
 # ---------------------------------------------------------------------------------------------

@@ -260,3 +260,40 @@ def test_two_gpu_sharding_matches_oracle():
                        cwd=root, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("ranks bitwise equal True") == 3
+
+
+@pytest.mark.parametrize("slots", [1, 2])
+def test_cross_validation_accuracy_matches_oracle(oracle, slots):
+    """north_star: identical per-site arg-max predictions and cross-validation accuracy. The
+    model on all sites + one model per fold through Classifier.buildClassifier (RemoveUseless,
+    standardisation and the null-model start recomputed on every training subset, as Weka's
+    crossValidateModel does), on identical fold index lists, against the same loop on the oracle;
+    slots = 2 trains the models side by side on one GPU."""
+    from sequnwinder_b200 import classifier as clf
+    p = make_problem("cfg1", 600)
+    counts = p.counts[:, p.keep[:80]]
+    T, A, S = 5, 8, 2
+    folds = clf.stratified_folds(p.cls, 3, seed=1)
+    cv = clf.cross_validate(p.crs, counts, p.cls, p.weights, p.num_classes, folds, slots=slots,
+                            ridge=10.0, pho=1.7, num_threads=T, admm_max_its=A,
+                            sequnwinder_max_its=S)
+    C = p.num_classes
+    want = np.full(len(p.cls), -1, dtype=np.int64)
+    for f, test in enumerate(folds):
+        train = np.setdiff1d(np.arange(len(p.cls)), test)
+        ct = counts[train]
+        keep = np.nonzero(ct.max(0) != ct.min(0))[0]
+        raw = np.concatenate([np.ones((train.size, 1)), ct[:, keep].astype(np.float64)], 1)
+        data, mean, sd = oracle.standardize(raw, p.weights[train])
+        x0, smx0 = oracle.init_params(p.cls[train], raw.shape[1], C, p.st)
+        xo, smo, tr = oracle.lone_execute(x0, smx0, data, p.cls[train], p.weights[train], p.st, C,
+                                          ridge=10.0, num_threads=T, admm_max_itr=A,
+                                          nodes_max_itr=S, host_threads=8)
+        assert np.array_equal(cv.fold_models[f].prep.keep, keep)
+        assert np.abs(cv.fold_models[f].x - xo).max() <= REL_TOL * np.abs(xo).max()
+        par = oracle.destandardize(xo, C, raw.shape[1], mean, sd)
+        raw_test = np.concatenate([np.ones((test.size, 1)), counts[test][:, keep].astype(np.float64)], 1)
+        want[test] = oracle.predict(par, raw_test).argmax(1)
+    assert np.array_equal(cv.predictions, want)                    # identical arg-max per site
+    assert cv.accuracy == float((want == p.cls).mean())            # identical CV accuracy
+    assert cv.full_model.m_Par.shape == (81, C)

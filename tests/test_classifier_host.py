@@ -38,3 +38,14 @@ def test_weight_rule():
         raise AssertionError("expected the 'Sum of weights' error (Classifier.java:359-362)")
     except ValueError as e:
         assert "Sum of weights" in str(e)
+
+
+def test_stratified_folds_partition_the_sites():
+    cls = np.array([0, 1, 2] * 11 + [0] * 4)
+    folds = clf.stratified_folds(cls, 3, seed=1)
+    assert sorted(np.concatenate(folds).tolist()) == list(range(cls.size))   # a partition
+    for c in range(3):                                                       # stratified
+        per = [int((cls[f] == c).sum()) for f in folds]
+        assert max(per) - min(per) <= 1
+    again = clf.stratified_folds(cls, 3, seed=1)
+    assert all(np.array_equal(a, b) for a, b in zip(folds, again))           # deterministic
