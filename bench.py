@@ -154,6 +154,26 @@ def cpu_oracle_sample(prep_data, x0, smx0, cls, w, crs, C, T, admm_iters, thread
     return nb * T * iters / tr.seconds_admm, tr.seconds_admm, iters, wall
 
 
+def oracle_kmer_all_cores(O, d, threads):
+    """The oracle's counting loop on `threads` host threads (contiguous row ranges; ctypes drops the
+    GIL during the call): SURVEY.md 8d asks for the path-1 CPU number single-threaded and on all cores."""
+    n = d.n_sites
+    bounds = np.linspace(0, n, threads + 1).astype(np.int64)
+
+    def work(a, b):
+        if b > a:
+            b0 = int(d.offsets[a])
+            O.kmer_count(d.bases[b0:int(d.offsets[b])], d.offsets[a:b + 1] - b0, KMIN, KMAX)
+
+    ths = [threading.Thread(target=work, args=(int(bounds[i]), int(bounds[i + 1]))) for i in range(threads)]
+    t0 = time.time()
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    return n * LENGTH / (time.time() - t0) / 1e9
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU algorithm for the path. The Java reference cannot
     be built in this image (no JDK; Weka and seqcode-core not vendored), so this is the oracle
@@ -179,10 +199,11 @@ def run_reference(args):
         if i >= args.warmup:
             vals.append(v)
             secs.append(s)
-    # k-mer path of the reference (counting loop only, single thread)
+    # k-mer path of the reference (counting loop only): single thread, and all host cores
     t0 = time.time()
     O.kmer_count(d.bases, d.offsets, KMIN, KMAX)
     kmer_gbs = d.n_sites * LENGTH / (time.time() - t0) / 1e9
+    kmer_gbs_all = oracle_kmer_all_cores(O, d, cores)
     value = float(np.mean(vals))
     sample = (f"first {sample_iters} ADMM iterations of outer iteration 1 on the full "
               f"{SITES_PER_GPU}x{prep.data.shape[1]} matrix, T={T} blocks on {threads} pthreads")
@@ -198,6 +219,7 @@ def run_reference(args):
                          "note": "CPU restatement of LOne.java (oracle/), not the JVM; the Java "
                                  "reference additionally sleeps >= 1 s per ADMM run (LOne.java:728-740)"},
         "kmer_gbases_per_s": kmer_gbs,
+        "kmer_gbases_per_s_all_cores": {"value": kmer_gbs_all, "cores": cores},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))

@@ -49,3 +49,52 @@ def test_stratified_folds_partition_the_sites():
         assert max(per) - min(per) <= 1
     again = clf.stratified_folds(cls, 3, seed=1)
     assert all(np.array_equal(a, b) for a, b in zip(folds, again))           # deterministic
+
+
+class _StubOptimizer:
+    """Stands in for LOneCuda in host-logic tests (no GPU here): records the calls and 'trains'
+    by writing a value derived from lambda and the CTA budget into x."""
+    made = []
+
+    def __init__(self, x, sm_x, data):
+        self.x, self.sm_x, self.data = x, sm_x, data
+        self.regularization, self._cta_budget, self._handle = 0.0, 0, None
+        self.stats, self.log = None, None
+        _StubOptimizer.made.append(self)
+
+    def __getattr__(self, name):          # every other setter is accepted and ignored
+        if name.startswith("set") or name in ("initUandZ", "clearOptimizer", "close"):
+            return lambda *a, **k: None
+        raise AttributeError(name)
+
+    def setRidge(self, r): self.regularization = float(r)
+    def setCtaBudget(self, b): self._cta_budget = int(b)
+
+    def execute(self):
+        if self.regularization < 0:
+            raise RuntimeError("negative lambda")
+        self.x[:] = self.regularization
+        self.sm_x[:] = self._cta_budget
+
+    def getX(self): return self.x
+    def getsmX(self): return self.sm_x
+
+
+def test_cross_validate_host_logic(monkeypatch):
+    """Task queue, CTA budgets, fold bookkeeping and pooled accuracy of cross_validate with a stub
+    trainer (the GPU parity of the same loop is tests/test_admm_gpu.py)."""
+    p = make_problem("cfg1", 300, max_features=20)
+    counts = p.counts[:, p.keep]
+    monkeypatch.setattr(clf, "LOneCuda", _StubOptimizer)
+    _StubOptimizer.made.clear()
+    folds = clf.stratified_folds(p.cls, 3)
+    cv = clf.cross_validate(p.crs, counts, p.cls, p.weights, p.num_classes, folds, slots=2, ridge=7.0)
+    assert len(_StubOptimizer.made) == 4                          # all sites + one per fold
+    assert {o._cta_budget for o in _StubOptimizer.made} == {148 // 2}
+    assert sorted(o.data.shape[0] for o in _StubOptimizer.made) == sorted(
+        [300] + [300 - len(f) for f in folds])                    # trained on the complement
+    assert (cv.predictions >= 0).all() and len(cv.fold_accuracy) == 3
+    hits = sum(a * len(f) for a, f in zip(cv.fold_accuracy, folds))
+    assert abs(cv.accuracy - hits / 300) < 1e-12                  # pooled over the folds
+    with np.testing.assert_raises(RuntimeError):                  # a worker's error reaches the caller
+        clf.cross_validate(p.crs, counts, p.cls, p.weights, p.num_classes, folds, slots=2, ridge=-1.0)
