@@ -713,7 +713,9 @@ static int plan_blocks(sqw_admm *h, int64_t n_rows, int32_t dim, int32_t num_cla
     int dimp8 = (dim + 7) / 8 * 8;
     if (((dimp8 / 8) & 1) == 0)
         dimp8 += 8;
-    const size_t budget = (size_t)prop.sharedMemPerBlockOptin - 8192;  // static SolveSmem etc.
+    // static shared memory of the x-update kernel (SolveSmem, tables, profile counters): 5.5 KB + 1 KB
+    // reserved by the driver
+    const size_t budget = (size_t)prop.sharedMemPerBlockOptin - (SQW_AUG_CACHE ? 7424 : 8192);
     // (one class tile: W lives in registers and the head of the layout is the solver's slice cache)
     TileSmemLayout L = tile_smem_layout(Cp, dimp4, budget, nct == 1 ? kSolveSliceBytes : 0);
     // single-pass tiles: one class tile only (with more the register-resident gradient

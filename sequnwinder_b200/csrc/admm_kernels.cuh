@@ -183,6 +183,49 @@ struct BlockProblem {
         return s;
     }
 
+    // The same term from inputs cached on chip (admm_solver.cuh, SQW_AUG_CACHE): aug_load fetches
+    // (sm_x[par], z, u_t) of the coordinate's edges once per launch, false if it has more than two;
+    // a parentless edge stores sm_x = +0.0 (x - 0.0 == x exactly). Same operations, same order.
+    __device__ bool aug_load(int k, double (&a)[6], int &ne)
+    {
+#pragma unroll
+        for (int j = 0; j < 6; ++j)
+            a[j] = 0.0;
+        ne = 0;
+        const int leaf = k / P.dimp, w = k - leaf * P.dimp;
+        if (w >= 1 && w < P.dim) {
+            const int e0 = lep[leaf], e1 = lep[leaf + 1];
+            if (e1 - e0 > 2)
+                return false;
+            ne = e1 - e0;
+            for (int j = 0; j < ne; ++j) {
+                const int e = e0 + j, par = epar[e];
+                const size_t o = (size_t)e * P.dimp + w;
+                a[3 * j] = (par >= 0) ? __ldg(P.smx + (size_t)par * P.dimp + w) : 0.0;
+                a[3 * j + 1] = __ldg(P.z + o);
+                a[3 * j + 2] = __ldcg(ut + o);
+            }
+        }
+        return true;
+    }
+    __device__ double aug_term_cached(double xk, const double (&a)[6], int ne, double &faug)
+    {
+        double s = 0.0;
+        if (ne >= 1) {
+            double v = xk - a[0];
+            v = (v - a[1]) + a[2];
+            s += pho * v;
+            faug += (pho / 2) * v * v;
+        }
+        if (ne == 2) {
+            double v = xk - a[3];
+            v = (v - a[4]) + a[5];
+            s += pho * v;
+            faug += (pho / 2) * v * v;
+        }
+        return s;
+    }
+
     __device__ double grad_coord(int k, double xk, double &faug)
     {
         const double a = aug_term(k, xk, faug);
@@ -276,6 +319,10 @@ admm_xupdate_kernel(AdmmDev P, TileSmemLayout L, int phase, int eval_cap)
 
     GroupBarrier gb{P.bar + ((size_t)phase * P.T_local + blk) * 32, 0u, G};
     __syncthreads();
+#if SQW_AUG_CACHE
+    if (!resume)
+        gb.sync();  // u_t complete in every CTA's slice before the solver caches its inputs
+#endif
     BlockProblem<Eval> prob{P, blk, cta, G, pho, ut, ev, sc.lep_p, sc.epar_p};
     SolveWs ws;
     ws.n = P.npad;
@@ -697,6 +744,8 @@ struct RosenProblem {
     static constexpr int kBatch = 1;
     __device__ void data_issue(int, double (&)[kBatch]) {}
     __device__ double data_finish(int, double (&)[kBatch]) { return 0.0; }
+    __device__ bool aug_load(int, double (&)[6], int &) { return false; }
+    __device__ double aug_term_cached(double, const double (&)[6], int, double &) { return 0.0; }
     __device__ double aug_term(int k, double, double &facc)
     {
         const int i = k >> 1;

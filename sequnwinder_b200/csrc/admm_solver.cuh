@@ -540,9 +540,18 @@ struct SolveWs {
                      // slice of x, d, g_old, wa, S, Y stays on chip for the whole launch
 };
 
-constexpr int kSliceCap = 320;                       // coordinates per CTA the slice cache holds
+#ifndef SQW_AUG_CACHE
+#define SQW_AUG_CACHE 0   // keep the augmented term's inputs (sm_x, z, u_t of a coordinate's edges) on chip too
+#endif
+#if SQW_AUG_CACHE
+constexpr int kSliceCap = 304;                       // coordinates per CTA the slice cache holds
+constexpr int kAugVectors = 6;                       // (sm_x[par], z, u_t) of up to two edges per coordinate
+#else
+constexpr int kSliceCap = 320;
+constexpr int kAugVectors = 0;
+#endif
 constexpr int kSliceVectors = 4 + 2 * kLbfgsM;       // x, d, g_old, wa, S[m], Y[m]
-constexpr size_t kSolveSliceBytes = (size_t)kSliceVectors * kSliceCap * sizeof(double);
+constexpr size_t kSolveSliceBytes = (size_t)(kSliceVectors + kAugVectors) * kSliceCap * sizeof(double);
 
 struct SolveSmem {
     double dots[kNumDots];
@@ -635,6 +644,22 @@ __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier 
             }
         }
     }
+    // the inputs of the augmented term are constant during the solve: with SQW_AUG_CACHE they are
+    // read once per launch; naug = number of cached edges of this thread's coordinate, -1 = not cached
+    int naug = -1;
+#if SQW_AUG_CACHE
+    double *const caug = cx + kSliceVectors * kSliceCap;
+    if (cached && mine) {
+        double a[6];
+        int ne = 0;
+        if (prob.aug_load(kf, a, ne)) {
+#pragma unroll
+            for (int j = 0; j < 6; ++j)
+                caug[j * kSliceCap] = a[j];
+            naug = ne;
+        }
+    }
+#endif
     __syncthreads();
     // history slots to reduce against (excludes the slot being replaced) / slot y_new is written to
     int point = resume ? st.point : 0;
@@ -679,6 +704,16 @@ __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier 
             }
         }
         c.faug = 0.0;
+#if SQW_AUG_CACHE
+        if (from_cache && naug >= 0) {
+            double a[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j)
+                a[j] = caug[j * kSliceCap];
+            c.gaug = prob.aug_term_cached(c.x, a, naug, c.faug);
+            return;
+        }
+#endif
         c.gaug = prob.aug_term(k, c.x, c.faug);
     };
 
