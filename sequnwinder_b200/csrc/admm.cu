@@ -98,6 +98,7 @@ struct sqw_admm {
     bool have_params = false, have_structure = false, have_problem = false, prepared = false;
     bool l2_persist = false;  // this handle set the device's persisting-L2 carve-out
     int cta_budget = 0;       // 0 = all SMs; else at most this many CTAs per x-update launch
+    bool unfused_tail = getenv("SQW_ADMM_UNFUSED") != nullptr;  // test hook: three-kernel iteration tail
     double ridge = 10.0, pho = 1.7;
     int T = 5, admm_max_itr = 400, nodes_max_itr = 15, debug = 0;
 
@@ -420,6 +421,16 @@ static int enqueue_iteration(sqw_admm *h, int slot)
     if ((rc = launch_xupdate(h)) != SQW_OK)
         return rc;
     SQW_CUDA_CHECK(cudaEventRecord(h->ev_x1[slot], h->stream));
+    if (h->world == 1 && !h->unfused_tail) {
+        // single GPU: pack + consensus + decide in one launch (admm_consensus_fused_kernel)
+        admm_consensus_fused_kernel<<<D.E, kThreads, 0, h->stream>>>(D);
+        SQW_CUDA_CHECK(cudaMemcpyAsync(&h->h_ring[slot], D.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost,
+                                       h->stream));
+        SQW_CUDA_CHECK(cudaEventRecord(h->ev_snap[slot], h->stream));
+        SQW_CUDA_CHECK(cudaGetLastError());
+        h->stats.launches += 2;
+        return SQW_OK;
+    }
     const int total = D.npad + D.upad;
     admm_pack_kernel<<<(total + 255) / 256, 256, 0, h->stream>>>(D);
     if ((rc = nccl_allreduce(h, D.sum1, (size_t)total)) != SQW_OK)

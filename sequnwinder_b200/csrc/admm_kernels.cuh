@@ -396,11 +396,11 @@ __global__ void __launch_bounds__(256) admm_pack_kernel(AdmmDev P)
 // LOne.java:670-716 restricted to edge e = (leaf, par): z_old <- z, x-bar, u-bar, x-hat, z,
 // soft-threshold with kappa = 2 lambda / (rho T) (intercept included), znorm (from u for a self
 // edge, :504), xnorm, dual residual term, and this rank's part of the primal residual term.
-__global__ void __launch_bounds__(kThreads) admm_consensus_kernel(AdmmDev P)
+// FUSED: the sums over the local blocks are formed here (same order as admm_pack_kernel) instead
+// of being read from sum1 - the single-GPU path, where no all-reduce sits between pack and consensus.
+template <bool FUSED>
+__device__ __forceinline__ void consensus_edge(const AdmmDev &P, double *red)
 {
-    __shared__ double red[kWarps];
-    if (ld_volatile_int(&P.ctrl->done) || ld_volatile_int(&P.ctrl->fatal))
-        return;
     const int e = blockIdx.x;
     const int leaf = P.edge_leaf[e], par = P.edge_par[e];
     const bool first_edge = (P.leaf_edge_ptr[leaf] == e);
@@ -410,8 +410,20 @@ __global__ void __launch_bounds__(kThreads) admm_consensus_kernel(AdmmDev P)
     double zn2 = 0, du2 = 0, xn2 = 0, pr2 = 0, cn2 = 0;
     for (int w = threadIdx.x; w < P.dim; w += blockDim.x) {
         const size_t o = (size_t)e * P.dimp + w, xo = (size_t)leaf * P.dimp + w;
-        const double xb = P.sum1[xo] / Td;
-        const double ub = P.sum1[P.npad + o] / Td;
+        double sx, su;
+        if (FUSED) {
+            sx = 0.0;
+            su = 0.0;
+            for (int b = 0; b < P.T_local; ++b) {  // local blocks are stored in summation order
+                sx += P.xt[(size_t)b * P.Cp * P.dimp + xo];
+                su += P.ut[(size_t)b * P.upad + o];
+            }
+        } else {
+            sx = P.sum1[xo];
+            su = P.sum1[P.npad + o];
+        }
+        const double xb = sx / Td;
+        const double ub = su / Td;
         const double zo = P.z[o];
         double smp = 0.0;
         double xhat = kAlpha * xb + (1 - kAlpha) * zo;
@@ -453,37 +465,43 @@ __global__ void __launch_bounds__(kThreads) admm_consensus_kernel(AdmmDev P)
     }
 }
 
+__global__ void __launch_bounds__(kThreads) admm_consensus_kernel(AdmmDev P)
+{
+    __shared__ double red[kWarps];
+    if (ld_volatile_int(&P.ctrl->done) || ld_volatile_int(&P.ctrl->fatal))
+        return;
+    consensus_edge<false>(P, red);
+}
+
 // ------------------------------------------------------------------ decide
 // The decision itself is the reference's serial bookkeeping and runs in one thread; but from
 // global memory it was ~140 dependent loads (20 us per ADMM iteration under ncu). The CTA first
 // stages every input in shared memory with one coalesced round trip, the other threads do the
 // per-block resets meanwhile, and thread 0 works on the staged copies.
 constexpr int kDecideThreads = 256;
-__global__ void __launch_bounds__(kDecideThreads) admm_decide_kernel(AdmmDev P)
+// (all threads of ONE CTA; inputs written by other CTAs are read with ld.cg)
+__device__ void decide_cta(const AdmmDev &P)
 {
     constexpr int kML = StructCache::kMaxLeaves, kME = StructCache::kMaxEdges;
+    const int kDecideThreads = (int)blockDim.x;
     __shared__ int s_lep[kML + 1], s_epar[kME], s_order[kME];
     __shared__ double s_xnorm[kML], s_sum2[kME], s_stats[4 * kME];
     __shared__ Ctrl s_ctrl;
     Ctrl *c = P.ctrl;
-    if (blockIdx.x != 0)
-        return;
-    if (ld_volatile_int(&c->done) || ld_volatile_int(&c->fatal))
-        return;
     const bool fits = P.C <= kML && P.E <= kME;
     const int tid = threadIdx.x;
     if (fits) {
         for (int i = tid; i <= P.C; i += kDecideThreads)
             s_lep[i] = P.leaf_edge_ptr[i];
         for (int i = tid; i < P.C; i += kDecideThreads)
-            s_xnorm[i] = P.leaf_xnorm[i];
+            s_xnorm[i] = __ldcg(P.leaf_xnorm + i);
         for (int i = tid; i < P.E; i += kDecideThreads) {
             s_epar[i] = P.edge_par[i];
             s_order[i] = P.edge_sum_order[i];
-            s_sum2[i] = P.sum2[i];
+            s_sum2[i] = __ldcg(P.sum2 + i);
         }
         for (int i = tid; i < 4 * P.E; i += kDecideThreads)
-            s_stats[i] = P.edge_stats[i];
+            s_stats[i] = __ldcg(P.edge_stats + i);
     }
     if (tid < (int)(sizeof(Ctrl) / sizeof(int)))
         reinterpret_cast<int *>(&s_ctrl)[tid] = reinterpret_cast<const int *>(c)[tid];
@@ -584,6 +602,41 @@ __global__ void __launch_bounds__(kDecideThreads) admm_decide_kernel(AdmmDev P)
     c->log_rows = lc.log_rows;
     c->total_evals = lc.total_evals;
     c->done = lc.done;
+}
+
+__global__ void __launch_bounds__(kDecideThreads) admm_decide_kernel(AdmmDev P)
+{
+    if (blockIdx.x != 0)
+        return;
+    if (ld_volatile_int(&P.ctrl->done) || ld_volatile_int(&P.ctrl->fatal))
+        return;
+    decide_cta(P);
+}
+
+// Single-GPU iteration tail in ONE launch: pack + consensus per edge, and the CTA that finishes
+// last (ticket counter in Ctrl) runs the decision. Same arithmetic in the same order as the three
+// kernels above, two launches and their gaps less per ADMM iteration.
+__global__ void __launch_bounds__(kThreads) admm_consensus_fused_kernel(AdmmDev P)
+{
+    __shared__ double red[kWarps];
+    __shared__ int s_last;
+    if (ld_volatile_int(&P.ctrl->done) || ld_volatile_int(&P.ctrl->fatal))
+        return;
+    consensus_edge<true>(P, red);
+    if (threadIdx.x == 0) {
+        __threadfence();  // this edge's statistics before the ticket
+        const unsigned t = atomicAdd(&P.ctrl->cons_count, 1u);
+        s_last = (t == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last)
+        return;
+    if (threadIdx.x == 0) {
+        P.ctrl->cons_count = 0u;
+        __threadfence();
+    }
+    __syncthreads();
+    decide_cta(P);
 }
 
 // ------------------------------------------------------------------ outer-iteration kernels

@@ -232,6 +232,19 @@ def test_concurrent_sweep_matches_budgeted_runs_and_oracle(oracle):
         assert np.abs(smx - smo).max() <= REL_TOL * np.abs(smo).max()
 
 
+def test_fused_iteration_tail_is_bit_identical(monkeypatch):
+    """Single GPU: pack + consensus + decide run as one launch (admm_consensus_fused_kernel); the
+    three-kernel tail (the multi-GPU path, SQW_ADMM_UNFUSED here) must give the same bits."""
+    p = make_problem("cfg1", 800, max_features=100)
+    fused = run_gpu(p, 5, 25, 3)
+    monkeypatch.setenv("SQW_ADMM_UNFUSED", "1")
+    plain = run_gpu(p, 5, 25, 3)
+    assert np.array_equal(fused.getX(), plain.getX()) and np.array_equal(fused.getsmX(), plain.getsmX())
+    assert np.array_equal(fused.log.pho, plain.log.pho) and np.array_equal(fused.log.primal, plain.log.primal)
+    assert np.array_equal(fused.log.nfev, plain.log.nfev)
+    assert fused.stats.launches < plain.stats.launches
+
+
 def test_errors_are_reported():
     p = make_problem("cfg1", 100, max_features=8)
     lo = opt.LOneCuda(p.x0.copy(), p.smx0.copy(), p.data)
