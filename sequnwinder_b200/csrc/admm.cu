@@ -84,7 +84,7 @@ static std::vector<int> java_thread_order(int T)
 constexpr int kNumPhases = 6;  // x-update launches per ADMM iteration (re-grouping points)
 constexpr int kRing = 8;       // Ctrl snapshots in flight
 #ifndef SQW_ADMM_FUSED_DEFAULT
-#define SQW_ADMM_FUSED_DEFAULT 0
+#define SQW_ADMM_FUSED_DEFAULT 1
 #endif
 constexpr int kLookahead = 3;  // iterations the host runs ahead of the snapshot it inspects
 
@@ -101,8 +101,7 @@ struct sqw_admm {
     bool have_params = false, have_structure = false, have_problem = false, prepared = false;
     bool l2_persist = false;  // this handle set the device's persisting-L2 carve-out
     int cta_budget = 0;       // 0 = all SMs; else at most this many CTAs per x-update launch
-    // iteration tail on one GPU: one fused launch unless SQW_ADMM_UNFUSED is set (test hook);
-    // SQW_ADMM_FUSED_DEFAULT is flipped only after the fused kernel passed the GPU parity tests
+    // iteration tail on one GPU: one fused launch unless SQW_ADMM_UNFUSED is set (test hook)
     bool unfused_tail = SQW_ADMM_FUSED_DEFAULT ? getenv("SQW_ADMM_UNFUSED") != nullptr
                                                : getenv("SQW_ADMM_FUSED") == nullptr;
     double ridge = 10.0, pho = 1.7;

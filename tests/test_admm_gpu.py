@@ -237,9 +237,7 @@ def test_fused_iteration_tail_is_bit_identical(monkeypatch):
     three-kernel tail (the multi-GPU path, SQW_ADMM_UNFUSED here) must give the same bits."""
     p = make_problem("cfg1", 800, max_features=100)
     monkeypatch.delenv("SQW_ADMM_UNFUSED", raising=False)
-    monkeypatch.setenv("SQW_ADMM_FUSED", "1")
     fused = run_gpu(p, 5, 25, 3)
-    monkeypatch.delenv("SQW_ADMM_FUSED")
     monkeypatch.setenv("SQW_ADMM_UNFUSED", "1")
     plain = run_gpu(p, 5, 25, 3)
     assert np.array_equal(fused.getX(), plain.getX()) and np.array_equal(fused.getsmX(), plain.getsmX())
