@@ -366,6 +366,8 @@ def main():
     my_bases = np.ascontiguousarray(d.bases[b_a:b_b])
     my_offs = np.ascontiguousarray(d.offsets[r_a:r_b + 1] - b_a)
 
+    kmer_host_s = []   # wall seconds of the host-buffer k-mer call of every e2e step (this rank's rows)
+
     def e2e_step():
         t0 = time.time()
         c, hn = kc.count(my_bases, my_offs)
@@ -379,6 +381,7 @@ def main():
         print(f"[bench] rank {info.rank} e2e step: k-mer (host buffers) {t1 - t0:.3f} s, upload "
               f"{t2 - t1:.3f} s, execute {dt - (t2 - t0):.3f} s (device {lo2.stats.seconds_total:.3f} s)",
               file=sys.stderr)
+        kmer_host_s.append(t1 - t0)
         return dt, lo2.stats.total_admm_iters, lo2.h2d_bytes, (c.nbytes + hn.nbytes) * world
 
     lo.close()
@@ -388,6 +391,7 @@ def main():
     if args.warmup > 0:
         e2e_step()  # untimed: the host-buffer path's one-time allocations (streams, staging buffers)
     barrier()
+    kmer_host_s.clear()
     for _ in range(e2e_steps):
         dt, it, hb, db = e2e_step()
         e2e_dt += dt
@@ -440,6 +444,9 @@ def main():
         "kmer_roofline": {"bound": "hbm", "achieved": kmer_bytes / kmer_s / 1e9, "peak": peak,
                           "unit": "GB/s", "frac": kmer_bytes / kmer_s / 1e9 / peak,
                           "note": "cfg-2 batch (102 MB of counts per pass): launch/latency bound"},
+        # the same featurisation through the host-buffer call (H2D of the bases, D2H
+        # of the count matrix to pageable memory inside the timing), rank 0's rows
+        "kmer_host_api_gbases_per_s": (r_b - r_a) * LENGTH * len(kmer_host_s) / max(sum(kmer_host_s), 1e-9) / 1e9,
         "kmer_stream": {"sites": ks_n, "gbases_per_s": ks_n * LENGTH / ks_sec / 1e9,
                         "bound": "hbm", "achieved": ks_n * (LENGTH + 4 * kc.numK) / ks_sec / 1e9,
                         "peak": peak, "unit": "GB/s",
