@@ -3,7 +3,7 @@
  * SeqUnwinder's two data-parallel hot paths. Plain pointers and sizes only; every entry point
  * names the reference interface it replaces. Citations are relative to
  * /root/reference/src/org/seqcode/projects/sequnwinder/. The Java-side JNI stubs that bind these
- * symbols are shown in INTEGRATION.md.
+ * symbols are jni/sequnwinder_b200_jni.c and the Java classes beside it, described in INTEGRATION.md.
  *
  * Conventions: every function returns SQW_OK (0) or a negative SQW_ERR_* code; the message for
  * the calling thread's last failure is sqw_last_error(). There is NO CPU fallback: without a
@@ -31,7 +31,7 @@ extern "C" {
 #define SQW_ERR_NCCL (-7)
 #define SQW_ERR_STATE (-8)        /* call sequence violated (e.g. execute before set_problem) */
 
-#define SQW_ABI_VERSION 1
+#define SQW_ABI_VERSION 2
 
 int sqw_abi_version(void);
 const char *sqw_last_error(void);
@@ -39,6 +39,10 @@ const char *sqw_last_error(void);
 int sqw_device_count(void);
 /* bind the calling thread (and handles created afterwards) to a device */
 int sqw_set_device(int device);
+/* the calling thread's current device (the CUDA current device is per host thread: a worker
+ * thread that creates handles must first sqw_set_device() the device of the thread that owns the
+ * data); -1 when there is no device */
+int sqw_get_device(void);
 
 /* ------------------------------------------------------------------------------------------
  * Path 1 — k-mer featurisation.
@@ -94,6 +98,32 @@ int sqw_admm_set_problem(sqw_admm *h, int64_t n_rows, int32_t dim, int32_t num_c
                          const double *data, const int32_t *y, const double *w);
 int sqw_admm_set_problem_dev(sqw_admm *h, int64_t n_rows, int32_t dim, int32_t num_classes,
                              const double *d_data, const int32_t *d_y, const double *d_w);
+
+/* The same problem in PACKED-COUNT form. SeqUnwinder's feature matrix is a matrix of k-mer
+ * counts (MakeArff.java:347-368: every feature is an integer in 0..L-k+1) that
+ * Classifier.buildClassifier standardises column by column (Classifier.java:362-381). Instead of
+ * the standardised doubles the caller hands over the counts and the column statistics:
+ *   counts : n_rows x (dim-1) uint8 row-major = m_Data[i][1..nR] BEFORE Classifier.java:373-381
+ *   mean, sd : dim doubles each = xMean / xSD of Classifier.java:362-371 (entry 0: 0 and 1)
+ * and the trainer evaluates LOne.OptObject (LOne.java:936-1049) on
+ *   X[i][j] = (counts[i][j-1] - mean[j]) / sd[j]   (the raw count where sd[j] == 0, :376)
+ * without ever materialising X: logits = counts . (W/sd) - sum_j mean_j W_j/sd_j and
+ * G = (R^T counts - mean (x) sum_i R_i) / sd, fp64 throughout. The matrix in HBM and shared memory
+ * is 8x smaller than the fp64 one, which turns the evaluation from HBM-bound into fp64-DMMA-bound
+ * (DESIGN.md 2.3). Relative to the fp64 entry point the results differ by rounding only (X is never
+ * rounded to fp64 element by element; the summation order differs as it does between any two
+ * group sizes). Returns SQW_ERR_UNSUPPORTED when the shape is outside what the packed kernels
+ * cover (then call sqw_admm_set_problem with the standardised matrix).
+ * _dev variant: the dense device count matrix of sqw_kmer_count_dev (n_rows x numK int32) plus
+ * the column plan of sqw_prepare_plan_dev (keep_idx[num_kept], mean / sd indexed by ORIGINAL
+ * column); dim = num_kept + 1. Counts above 255 -> SQW_ERR_UNSUPPORTED. Synchronises `stream`. */
+int sqw_admm_set_problem_counts(sqw_admm *h, int64_t n_rows, int32_t dim, int32_t num_classes,
+                                const uint8_t *counts, const double *mean, const double *sd,
+                                const int32_t *y, const double *w);
+int sqw_admm_set_problem_counts_dev(sqw_admm *h, int64_t n_rows, int64_t numK, int32_t num_classes,
+                                    const int32_t *d_counts, const int32_t *d_keep_idx,
+                                    int32_t num_kept, const double *d_mean, const double *d_sd,
+                                    const int32_t *d_y, const double *d_w, void *stream);
 
 /* setClassStructure (LOne.java:99; Classifier.java:633-736), CSR arrays with one entry per
  * design-file line in file order. Parents are meaningful for leaves only, children for
@@ -155,6 +185,14 @@ typedef struct {
     int64_t launches;         /* kernels launched by execute */
     double seconds_eval;      /* device time of the x-update kernels only */
     int64_t eval_bytes;       /* algorithmic bytes read by those kernels */
+    /* which evaluation path ran (tests assert that the path a benchmark uses is the path they
+     * compared with the oracle): */
+    int32_t eval_mode;        /* 4/5 fp64 single-pass TMA tiles, 6 fp64 column-chunked, 1/2 fp64
+                                 streaming, 8/9 packed-count (uint8) tiles */
+    int32_t ctas_per_block;   /* CTAs of a block's group while every local block is active */
+    int32_t ring_stages;      /* tile stages of the TMA ring in shared memory */
+    int32_t tiles_per_cta;    /* tiles a CTA walks per evaluation pass; > ring_stages means the
+                                 ring streams (refill path), <= means its rows stay resident */
 } sqw_admm_stats;
 int sqw_admm_get_stats(const sqw_admm *h, sqw_admm_stats *out);
 

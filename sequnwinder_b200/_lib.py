@@ -35,6 +35,7 @@ SYMBOLS = {
     "sqw_last_error": (C.c_char_p, []),
     "sqw_device_count": (C.c_int, []),
     "sqw_set_device": (C.c_int, [C.c_int]),
+    "sqw_get_device": (C.c_int, []),
     "sqw_num_kmers": (C.c_int64, [C.c_int, C.c_int]),
     "sqw_kmer_count": (C.c_int, [C.c_void_p, i64p, C.c_int64, C.c_int, C.c_int, i32p, u8p]),
     "sqw_kmer_count_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int,
@@ -80,7 +81,9 @@ class AdmmStats(C.Structure):
                 ("final_pho", C.c_double), ("final_fold", C.c_double),
                 ("seconds_admm", C.c_double), ("seconds_total", C.c_double),
                 ("launches", C.c_int64), ("seconds_eval", C.c_double),
-                ("eval_bytes", C.c_int64)]
+                ("eval_bytes", C.c_int64), ("eval_mode", C.c_int32),
+                ("ctas_per_block", C.c_int32), ("ring_stages", C.c_int32),
+                ("tiles_per_cta", C.c_int32)]
 
 
 class SqwError(RuntimeError):

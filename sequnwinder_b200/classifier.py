@@ -216,9 +216,14 @@ def cross_validate(structure: ClassRelationStructure, counts: np.ndarray, cls: n
         tasks.put((f, train))
     models: Dict[int, Classifier] = {}
     errors: list = []
+    # the CUDA current device is per host thread: workers train on the caller's device
+    from . import _lib
+    parent_dev = _lib.load().sqw_get_device()
 
     def worker():
         try:
+            if parent_dev >= 0:
+                _lib.check(_lib.load().sqw_set_device(parent_dev))
             while not errors:
                 try:
                     f, rows = tasks.get_nowait()
@@ -231,11 +236,14 @@ def cross_validate(structure: ClassRelationStructure, counts: np.ndarray, cls: n
         except Exception as exc:  # surfaced to the caller below
             errors.append(exc)
 
-    threads = [threading.Thread(target=worker) for _ in range(slots)]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
+    if slots == 1:
+        worker()              # inline, on the calling thread
+    else:
+        threads = [threading.Thread(target=worker) for _ in range(slots)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
     if errors:
         raise errors[0]
     pred = np.full(n, -1, dtype=np.int64)

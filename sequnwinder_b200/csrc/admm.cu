@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -35,9 +36,8 @@ struct NcclApi {
 static NcclApi *nccl_api()
 {
     static NcclApi api;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    static std::once_flag once;
+    std::call_once(once, [] {
         const char *names[] = {"libnccl.so.2", "libnccl.so"};
         for (const char *nm : names) {
             api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
@@ -52,7 +52,7 @@ static NcclApi *nccl_api()
             api.CommDestroy = (int (*)(void *))dlsym(api.lib, "ncclCommDestroy");
             api.GetErrorString = (const char *(*)(int))dlsym(api.lib, "ncclGetErrorString");
         }
-    }
+    });
     if (!api.lib || !api.GetUniqueId || !api.CommInitRank || !api.AllReduce)
         return nullptr;
     return &api;
@@ -128,7 +128,12 @@ struct sqw_admm {
     AdmmDev dev{};
     Ctrl *h_ring = nullptr;  // pinned [kRing]
     cudaEvent_t ev_x0[kRing], ev_x1[kRing], ev_snap[kRing];
-    cudaEvent_t ev_a, ev_b;
+    cudaEvent_t ev_a, ev_b, ev_t0, ev_t1;
+    // evaluation caps of the x-update phases (cumulative; the last phase runs every block to
+    // completion); tuned at cfg-2 (mean 14.7, max 24 evaluations per x-update)
+    int caps[kNumPhases] = {8, 12, 16, 20, 26, 0x7fffffff};
+    int nphase = kNumPhases;   // launches per x-update (1 when the rank owns a single block)
+    int tile_rows = 8;         // rows per tile of the evaluation path in use
     int eval_mode = -1;        // 0 TMA tiles, 1 streaming + W in smem, 2 streaming + W global
     int force_mode = -1;       // test hook (SQW_ADMM_EVAL_MODE)
     size_t xupdate_smem = 0;
@@ -250,10 +255,19 @@ static int prepare(sqw_admm *h)
         h->xupdate_smem = 0;
     XKernel xk = xupdate_kernel(nct, mode);
     EKernel ek = eval_kernel(nct, mode);
-    SQW_CUDA_CHECK(cudaFuncSetAttribute(xk, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)h->xupdate_smem));
-    SQW_CUDA_CHECK(cudaFuncSetAttribute(ek, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)h->xupdate_smem));
+    // The attribute is per function and process-wide: handles of different shapes (the folds of a
+    // cross-validation, two resident optimizers) share the kernels, so it is always raised to the
+    // device's opt-in maximum and each launch passes its own size.
+    // (dynamic + static shared memory of a kernel may not exceed the opt-in limit)
+    for (const void *fn : {(const void *)xk, (const void *)ek}) {
+        cudaFuncAttributes fa;
+        SQW_CUDA_CHECK(cudaFuncGetAttributes(&fa, fn));
+        const size_t dyn_max = (size_t)prop.sharedMemPerBlockOptin - fa.sharedSizeBytes;
+        if (h->xupdate_smem > dyn_max)
+            return set_error(SQW_ERR_UNSUPPORTED, "x-update needs %zu bytes of shared memory (max %zu)",
+                             h->xupdate_smem, dyn_max);
+        SQW_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_max));
+    }
     int per_sm = 0;
     SQW_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, xk, kThreads,
                                                                  h->xupdate_smem));
@@ -269,9 +283,9 @@ static int prepare(sqw_admm *h)
     }
     const int max_useful = std::max(1, (D.nb + 7) / 8);
     G = std::min(G, max_useful);
-    D.G = G;
-    D.Gmax = G * D.T_local;
-    D.nphase = kNumPhases;
+    // a rank that owns a single block has nothing to re-group: one launch, run to completion
+    h->nphase = (D.T_local == 1) ? 1 : kNumPhases;
+    D.nphase = h->nphase;
     // measured at cfg-2 (2 500 rows per block; tools/gcap.sh): 64.5 us per evaluation round
     // without a cap, 62.0 with 48, 63.6 with 36, 66.8 with 24. A trip costs ~ rows/G of evaluation
     // plus ~ G of partial-gradient exchange (both scale with C * dim), so the best G grows with
@@ -279,6 +293,10 @@ static int prepare(sqw_admm *h)
     // SQW_ADMM_GCAP is the tuning hook.
     const int gcap_auto = std::max(16, (int)(0.96 * std::sqrt((double)D.nb) + 0.5));
     D.gcap = getenv("SQW_ADMM_GCAP") ? std::max(1, atoi(getenv("SQW_ADMM_GCAP"))) : gcap_auto;
+    if (D.T_local == 1)
+        G = std::min(G, D.gcap);
+    D.G = G;
+    D.Gmax = G * D.T_local;
 
     int rc;
 #define TRY(x)            \
@@ -371,6 +389,8 @@ static int prepare(sqw_admm *h)
     }
     SQW_CUDA_CHECK(cudaEventCreate(&h->ev_a));
     SQW_CUDA_CHECK(cudaEventCreate(&h->ev_b));
+    SQW_CUDA_CHECK(cudaEventCreate(&h->ev_t0));
+    SQW_CUDA_CHECK(cudaEventCreate(&h->ev_t1));
     h->prepared = true;
     return SQW_OK;
 }
@@ -379,29 +399,13 @@ static int launch_xupdate(sqw_admm *h)
 {
     AdmmDev &D = h->dev;
     XKernel xk = xupdate_kernel(D.Cp / 8, h->eval_mode);
-    // evaluation caps of the phases (cumulative); the last phase runs every block to completion
-    static int caps[kNumPhases] = {8, 12, 16, 20, 26, 0x7fffffff};  // tuned at cfg-2 (mean 14.7, max 24 evaluations)
-    static bool caps_init = false;
-    if (!caps_init) {
-        caps_init = true;
-        if (const char *env = getenv("SQW_ADMM_CAPS")) {  // tuning hook: comma separated caps
-            int i = 0;
-            for (const char *q = env; *q && i < kNumPhases - 1; ++i) {
-                caps[i] = atoi(q);
-                while (*q && *q != ',')
-                    ++q;
-                if (*q == ',')
-                    ++q;
-            }
-        }
-    }
-    for (int ph = 0; ph < kNumPhases; ++ph) {
-        int phase = ph, cap = caps[ph];
+    for (int ph = 0; ph < h->nphase; ++ph) {
+        int phase = ph, cap = (ph == h->nphase - 1) ? 0x7fffffff : h->caps[ph];
         void *args[] = {&D, &h->layout, &phase, &cap};
         SQW_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)xk, dim3(D.Gmax), dim3(kThreads), args,
                                                    h->xupdate_smem, h->stream));
     }
-    h->stats.launches += kNumPhases - 1;
+    h->stats.launches += h->nphase - 1;
     return SQW_OK;
 }
 
@@ -466,6 +470,16 @@ int sqw_admm_create(sqw_admm **out)
     sqw_admm *h = new sqw_admm();
     SQW_CUDA_CHECK(cudaGetDevice(&h->device));
     SQW_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    if (const char *env = getenv("SQW_ADMM_CAPS")) {  // tuning hook (header): comma separated caps
+        int i = 0;
+        for (const char *q = env; *q && i < kNumPhases - 1; ++i) {
+            h->caps[i] = atoi(q);
+            while (*q && *q != ',')
+                ++q;
+            if (*q == ',')
+                ++q;
+        }
+    }
     *out = h;
     return SQW_OK;
 }
@@ -493,6 +507,8 @@ void sqw_admm_destroy(sqw_admm *h)
         }
         cudaEventDestroy(h->ev_a);
         cudaEventDestroy(h->ev_b);
+        cudaEventDestroy(h->ev_t0);
+        cudaEventDestroy(h->ev_t1);
     }
     if (h->stream)
         cudaStreamDestroy(h->stream);
@@ -665,6 +681,8 @@ int sqw_admm_set_comm(sqw_admm *h, int32_t rank, int32_t world, const uint8_t nc
         void *comm;
     };
     static std::vector<Cached> cache;
+    static std::mutex cache_mu;
+    std::lock_guard<std::mutex> lock(cache_mu);
     const std::string key(reinterpret_cast<const char *>(nccl_id), 128);
     for (const Cached &c : cache)
         if (c.id == key) {
@@ -874,11 +892,25 @@ static int download_padded(sqw_admm *h, const double *src, int rows, int dim, in
     return SQW_OK;
 }
 
+static int execute_impl(sqw_admm *h, double *x_inout, double *smx_inout);
+
 int sqw_admm_execute(sqw_admm *h, double *x_inout, double *smx_inout)
 {
     if (!h || !x_inout || !smx_inout)
         return set_error(SQW_ERR_INVALID_ARG, "null argument");
     SQW_CUDA_CHECK(cudaSetDevice(h->device));
+    const int rc = execute_impl(h, x_inout, smx_inout);
+    if (rc != SQW_OK && h->stream) {
+        // an error path may leave speculatively enqueued iterations behind: let them finish (their
+        // kernels return at once when Ctrl.done / fatal is set) before the caller touches the handle
+        cudaStreamSynchronize(h->stream);
+        cudaGetLastError();
+    }
+    return rc;
+}
+
+static int execute_impl(sqw_admm *h, double *x_inout, double *smx_inout)
+{
     int rc = prepare(h);
     if (rc != SQW_OK)
         return rc;
@@ -904,9 +936,7 @@ int sqw_admm_execute(sqw_admm *h, double *x_inout, double *smx_inout)
     h->stats = sqw_admm_stats{};
     h->admm_iters.clear();
     double ms_admm = 0.0, ms_eval = 0.0;
-    cudaEvent_t ev_t0, ev_t1;
-    SQW_CUDA_CHECK(cudaEventCreate(&ev_t0));
-    SQW_CUDA_CHECK(cudaEventCreate(&ev_t1));
+    cudaEvent_t ev_t0 = h->ev_t0, ev_t1 = h->ev_t1;
     SQW_CUDA_CHECK(cudaEventRecord(ev_t0, st));
     Ctrl last = c0;
     bool converged = false;
@@ -985,8 +1015,6 @@ int sqw_admm_execute(sqw_admm *h, double *x_inout, double *smx_inout)
     SQW_CUDA_CHECK(cudaEventSynchronize(ev_t1));
     float ms_total = 0.f;
     SQW_CUDA_CHECK(cudaEventElapsedTime(&ms_total, ev_t0, ev_t1));
-    cudaEventDestroy(ev_t0);
-    cudaEventDestroy(ev_t1);
 
     if ((rc = download_padded(h, D.xbar, D.C, D.dim, D.dimp, x_inout)) != SQW_OK) return rc;
     if ((rc = download_padded(h, D.smx, D.NN, D.dim, D.dimp, smx_inout)) != SQW_OK) return rc;
@@ -1053,6 +1081,13 @@ int sqw_admm_execute(sqw_admm *h, double *x_inout, double *smx_inout)
     const long long b_eval = 2ll * D.nb * D.dim * 8 + 2ll * D.nb * D.C * 8 + 12ll * D.nb +
                              2ll * D.C * D.dim * 8;
     h->stats.eval_bytes = last.total_evals * b_eval;
+    h->stats.eval_mode = h->eval_mode;
+    h->stats.ctas_per_block = D.G;
+    h->stats.ring_stages = h->layout.NS;
+    {   // tiles of the busiest CTA of a group (cta_row_range: whole tiles dealt out evenly)
+        const long long tiles = (D.nb + h->tile_rows - 1) / h->tile_rows;
+        h->stats.tiles_per_cta = (int)((tiles + D.G - 1) / D.G);
+    }
     if (last.fatal)
         return set_error(SQW_ERR_NUMERIC, "NaN/Inf met by the solver (the reference would have thrown, LBFGS.java:792-814)");
     return SQW_OK;

@@ -1,0 +1,336 @@
+// admm_eval_packed.cuh — (objective, gradient) evaluation on the PACKED count matrix (MODE 8).
+//
+// SeqUnwinder's training matrix is a matrix of k-mer counts (loaddata/MakeArff.java:347-368: every
+// feature is an integer 0..L-k+1) that Classifier.buildClassifier standardises column by column
+// (framework/Classifier.java:362-381). The fp64 modes stream the standardised doubles from HBM on
+// every evaluation (8 bytes per element, 104 MB per evaluation round at cfg-2). Here the CTA keeps
+// its rows of the block as the ORIGINAL counts, one byte per element, in shared memory for the
+// whole launch (cfg-2: 144 rows x 656 B = 94 KB) and evaluates LOne.OptObject
+// (framework/LOne.java:936-1049) on X[i][j] = (n[i][j] - mean[j]) / sd[j] without materialising X:
+//
+//     s[i][c]  = sum_j n[i][j] V[c][j] - o[c],   V[c][j] = W[c][j] / sd[j],  o[c] = sum_j mean[j] V[c][j]
+//     G[c][j]  = (sum_i R[i][c] n[i][j] - mean[j] sum_i R[i][c]) / sd[j],    R = diag(w)(P - Y)
+//
+// (column 0 of the packed matrix is the constant 1 of Classifier.java:340 with mean 0, sd 1, so the
+// intercept is an ordinary column and sum_i R[i][c] is the column-0 entry of the first product).
+// All arithmetic is fp64; counts convert exactly. The products are the same DMMA m8n8k4 passes as
+// the fp64 modes, but nothing crosses HBM after the launch prologue and nothing waits on a tile:
+//
+//   pass 1   all tiles: partial logits per DMMA warp (K split over the 8 warps by 16-column groups:
+//            one LDS.32 = 4 k-steps of one row) -> shared memory
+//   softmax  all 11 warps: sum of the 8 K-slices, max-shifted softmax, residuals R, NLL
+//   pass 2   all tiles: G += R^T n with the accumulators in registers (one LDS.U16 = 2 columns)
+//   epilogue the mean / sd correction of the CTA's partial gradient, one store
+//
+// three __syncthreads per evaluation instead of two named-barrier hand-offs per 8-row tile.
+// Relative to the fp64 modes the result differs by rounding only (X is never rounded element by
+// element); against the oracle one evaluation agrees to ~1e-15 relative.
+#pragma once
+
+#include "admm_eval_tma.cuh"
+
+namespace sqw {
+
+constexpr int kPackedNBG = 6;                       // 16-column groups per DMMA warp
+constexpr int kPackedMaxDim = 8 * kPackedNBG * 16;  // 768 columns incl. the intercept
+
+// no L2 hint: the packed matrix (13 MB at cfg-2) stays in L2 between the launches of an iteration
+__device__ __forceinline__ void bulk_g2s_plain(void *dst, const void *src, unsigned bytes,
+                                               unsigned long long *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// Shared-memory carve-up (TileSmemLayout re-used): head = the solver's slice cache, stage = the
+// CTA's rows (rows_cap8 x rsq bytes), plog = [8 warps][rows_cap8][8] partial logits (slot 0 is
+// re-used for the residuals), rs = 8 x 8 offset partials + 8 class sums, bar = one mbarrier.
+inline TileSmemLayout packed_smem_layout(int rsq, int rows_cap8, size_t slice_bytes)
+{
+    TileSmemLayout L{};
+    L.w_off = 0;
+    L.w_bytes = (slice_bytes + 127) & ~(size_t)127;
+    L.stage_off = L.w_bytes;
+    L.stage_bytes = ((size_t)rows_cap8 * rsq + 127) & ~(size_t)127;
+    L.plog_off = L.stage_off + L.stage_bytes;
+    L.rs_off = L.plog_off + (size_t)kDmmaWarps * rows_cap8 * 8 * sizeof(double);
+    L.bar_off = L.rs_off + (kDmmaWarps * 8 + 8) * sizeof(double);
+    L.total = L.bar_off + 128;
+    L.NS = rows_cap8 / kTileRows;  // tiles the resident buffer holds
+    return L;
+}
+
+__device__ __forceinline__ double cvt_u8(unsigned v)
+{
+    return __uint2double_rn(v);
+}
+
+template <int NCT>
+struct PackedEval {
+    static_assert(NCT == 1, "packed evaluation: one class tile");
+    static constexpr int NBG = kPackedNBG;
+    const AdmmDev &P;
+    int blk, cta, G;
+    unsigned char *rows;
+    double *plog, *scr;
+    unsigned long long *full;
+    double *red;
+    int cap8, r0, r1, ntiles, rsq;
+    bool loaded;
+    long long *prof;
+
+    __device__ void init(unsigned char *smem, const TileSmemLayout &L, double *red_)
+    {
+        rows = smem + L.stage_off;
+        plog = reinterpret_cast<double *>(smem + L.plog_off);
+        scr = reinterpret_cast<double *>(smem + L.rs_off);
+        full = reinterpret_cast<unsigned long long *>(smem + L.bar_off);
+        red = red_;
+        cap8 = L.NS * kTileRows;
+        rsq = P.rsq;
+        cta_row_range(P, cta, G, r0, r1);
+        ntiles = max(0, (r1 - r0 + kTileRows - 1) / kTileRows);
+        loaded = false;
+        prof = nullptr;
+        if (threadIdx.x == 0) {
+            mbar_init(&full[0], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && ntiles > 0) {
+            // the CTA's rows are contiguous in the block-major matrix: a few large bulk copies
+            const unsigned total = (unsigned)(r1 - r0) * (unsigned)rsq;
+            const unsigned char *src = P.Xq + ((size_t)blk * P.nb + r0) * rsq;
+            mbar_expect_tx(&full[0], total);
+            constexpr unsigned kChunk = 16384;
+            for (unsigned o = 0; o < total; o += kChunk)
+                bulk_g2s_plain(rows + o, src + o, min(kChunk, total - o), &full[0]);
+        }
+    }
+
+    __device__ void set_profile(long long *p) { prof = p; }
+
+    __device__ void drain()
+    {
+        if (!loaded && ntiles > 0)
+            mbar_wait(&full[0], 0);
+    }
+
+    __device__ double eval(const double *xcur)
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int qd = lane & 3, gid = lane >> 2;
+        const int dimp = P.dimp;
+        const int ngroups = dimp >> 4;
+        long long tk0 = 0, tk1 = 0;
+        const bool do_prof = prof != nullptr && threadIdx.x == 0;
+        if (do_prof)
+            tk0 = sqw_now_ns();
+#define SQW_EPROF(slot)          \
+    if (do_prof) {               \
+        tk1 = sqw_now_ns();      \
+        prof[slot] += tk1 - tk0; \
+        tk0 = tk1;               \
+    }
+        double *rres = plog;  // residuals overwrite K-slice 0 of the partial logits, row by row
+
+        // ---------------- pass 1: partial logits of every tile ----------------
+        if (warp < kDmmaWarps) {
+            // V[class gid][16 g + 4 qd + t] = W / sd for this warp's column groups, and the warp's
+            // part of the offset o[class] = sum_j mean[j] V[class][j]
+            double wreg[NBG * 4];
+            double pb = 0.0;
+#pragma unroll
+            for (int i = 0; i < NBG; ++i) {
+                const int g = warp + kDmmaWarps * i;
+                const int col = 16 * g + 4 * qd;
+                double2 w01 = make_double2(0.0, 0.0), w23 = w01, s01 = w01, s23 = w01, m01 = w01, m23 = w01;
+                if (g < ngroups) {
+                    s01 = __ldg(reinterpret_cast<const double2 *>(P.cinvsd + col));
+                    s23 = __ldg(reinterpret_cast<const double2 *>(P.cinvsd + col + 2));
+                    m01 = __ldg(reinterpret_cast<const double2 *>(P.cmean + col));
+                    m23 = __ldg(reinterpret_cast<const double2 *>(P.cmean + col + 2));
+                    if (gid < P.C) {
+                        const double *wg = xcur + (size_t)gid * dimp + col;
+                        w01 = __ldcg(reinterpret_cast<const double2 *>(wg));
+                        w23 = __ldcg(reinterpret_cast<const double2 *>(wg + 2));
+                    }
+                }
+                wreg[4 * i + 0] = w01.x * s01.x;
+                wreg[4 * i + 1] = w01.y * s01.y;
+                wreg[4 * i + 2] = w23.x * s23.x;
+                wreg[4 * i + 3] = w23.y * s23.y;
+                pb += m01.x * wreg[4 * i + 0];
+                pb += m01.y * wreg[4 * i + 1];
+                pb += m23.x * wreg[4 * i + 2];
+                pb += m23.y * wreg[4 * i + 3];
+            }
+            pb += __shfl_xor_sync(0xffffffffu, pb, 1);
+            pb += __shfl_xor_sync(0xffffffffu, pb, 2);
+            if (qd == 0)
+                scr[warp * 8 + gid] = pb;
+            SQW_EPROF(0)
+            if (!loaded && ntiles > 0)
+                mbar_wait(&full[0], 0);
+            SQW_EPROF(1)
+            const bool last_group = warp + kDmmaWarps * (NBG - 1) < ngroups;
+#pragma unroll 2
+            for (int j = 0; j < ntiles; ++j) {
+                const unsigned char *rp = rows + (size_t)(kTileRows * j + gid) * rsq + 4 * qd;
+                unsigned wv[NBG];
+#pragma unroll
+                for (int i = 0; i < NBG; ++i) {
+                    const int g = warp + kDmmaWarps * i;
+                    wv[i] = (g < ngroups) ? *reinterpret_cast<const unsigned *>(rp + 16 * g) : 0u;
+                }
+                double pa[4][2];
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    pa[c][0] = pa[c][1] = 0.0;
+#pragma unroll
+                for (int i = 0; i < NBG; ++i) {
+                    if (i == NBG - 1 && !last_group)  // warp-uniform: only a warp's last group can be absent
+                        break;
+                    dmma884(pa[0], cvt_u8(wv[i] & 0xffu), wreg[4 * i + 0]);
+                    dmma884(pa[1], cvt_u8((wv[i] >> 8) & 0xffu), wreg[4 * i + 1]);
+                    dmma884(pa[2], cvt_u8((wv[i] >> 16) & 0xffu), wreg[4 * i + 2]);
+                    dmma884(pa[3], cvt_u8(wv[i] >> 24), wreg[4 * i + 3]);
+                }
+                // lane holds the partial S[row gid][class 2 qd + {0, 1}]
+                *reinterpret_cast<double2 *>(plog + ((size_t)warp * cap8 + kTileRows * j + gid) * 8 + 2 * qd) =
+                    make_double2((pa[0][0] + pa[1][0]) + (pa[2][0] + pa[3][0]),
+                                 (pa[0][1] + pa[1][1]) + (pa[2][1] + pa[3][1]));
+            }
+        }
+        loaded = true;
+        __syncthreads();
+        SQW_EPROF(2)
+
+        // ---------------- softmax of every row: residuals, NLL ----------------
+        double facc = 0.0;
+        {
+            double o0 = 0.0, o1 = 0.0;
+#pragma unroll
+            for (int w8 = 0; w8 < kDmmaWarps; ++w8) {
+                o0 += scr[w8 * 8 + 2 * qd];
+                o1 += scr[w8 * 8 + 2 * qd + 1];
+            }
+            const int *yb = P.y + (size_t)blk * P.nb;
+            const double *wb = P.w + (size_t)blk * P.nb;
+            for (int j = warp; j < ntiles; j += kWarps) {
+                const int lr = kTileRows * j + gid;
+                const int row = r0 + lr;
+                const bool rv = row < r1;
+                const int rowc = rv ? row : r0;
+                const int cls = yb[rowc];
+                const double wi = wb[rowc];
+                double2 v = *reinterpret_cast<const double2 *>(plog + (size_t)lr * 8 + 2 * qd);
+#pragma unroll
+                for (int w8 = 1; w8 < kDmmaWarps; ++w8) {
+                    const double2 pv =
+                        *reinterpret_cast<const double2 *>(plog + ((size_t)w8 * cap8 + lr) * 8 + 2 * qd);
+                    v.x += pv.x;
+                    v.y += pv.y;
+                }
+                v.x -= o0;
+                v.y -= o1;
+                double mx = -INFINITY;
+                if (2 * qd < P.C)
+                    mx = fmax(mx, v.x);
+                if (2 * qd + 1 < P.C)
+                    mx = fmax(mx, v.y);
+                mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                const double e0 = (2 * qd < P.C) ? exp(v.x - mx) : 0.0;
+                const double e1 = (2 * qd + 1 < P.C) ? exp(v.y - mx) : 0.0;
+                double den = e0 + e1;
+                den += __shfl_xor_sync(0xffffffffu, den, 1);
+                den += __shfl_xor_sync(0xffffffffu, den, 2);
+                double rr0 = wi * (e0 / den), rr1 = wi * (e1 / den);
+                if (2 * qd == cls)
+                    rr0 -= wi;
+                if (2 * qd + 1 == cls)
+                    rr1 -= wi;
+                *reinterpret_cast<double2 *>(rres + (size_t)lr * 8 + 2 * qd) =
+                    rv ? make_double2(rr0, rr1) : make_double2(0.0, 0.0);
+                const double logden = log(den);
+                if (rv && 2 * qd == cls)
+                    facc -= wi * ((v.x - mx) - logden);
+                if (rv && 2 * qd + 1 == cls)
+                    facc -= wi * ((v.y - mx) - logden);
+            }
+        }
+        __syncthreads();
+        SQW_EPROF(3)
+
+        // ---------------- pass 2: G += R^T n over every tile ----------------
+        double acc[NBG][2][2];
+#pragma unroll
+        for (int i = 0; i < NBG; ++i)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                acc[i][h][0] = acc[i][h][1] = 0.0;
+        if (warp < kDmmaWarps) {
+            const bool last_group = warp + kDmmaWarps * (NBG - 1) < ngroups;
+#pragma unroll 2
+            for (int j = 0; j < ntiles; ++j) {
+                const double a0 = rres[(size_t)(kTileRows * j + qd) * 8 + gid];      // R[row qd][class gid]
+                const double a1 = rres[(size_t)(kTileRows * j + 4 + qd) * 8 + gid];  // R[row 4+qd][class gid]
+                const unsigned char *rp0 = rows + (size_t)(kTileRows * j + qd) * rsq + 2 * gid;
+                const unsigned char *rp1 = rp0 + 4 * (size_t)rsq;
+                unsigned x0[NBG], x1[NBG];
+#pragma unroll
+                for (int i = 0; i < NBG; ++i) {
+                    const int g = warp + kDmmaWarps * i;
+                    x0[i] = (g < ngroups) ? *reinterpret_cast<const unsigned short *>(rp0 + 16 * g) : 0u;
+                    x1[i] = (g < ngroups) ? *reinterpret_cast<const unsigned short *>(rp1 + 16 * g) : 0u;
+                }
+#pragma unroll
+                for (int i = 0; i < NBG; ++i) {
+                    if (i == NBG - 1 && !last_group)
+                        break;
+                    dmma884(acc[i][0], a0, cvt_u8(x0[i] & 0xffu));
+                    dmma884(acc[i][1], a0, cvt_u8(x0[i] >> 8));
+                    dmma884(acc[i][0], a1, cvt_u8(x1[i] & 0xffu));
+                    dmma884(acc[i][1], a1, cvt_u8(x1[i] >> 8));
+                }
+            }
+            // lane holds sum_i R[i][class gid] n[i][16 g + 4 qd + 2 e + h] in acc[i][h][e]; column 0
+            // (g = 0: warp 0, qd = 0, h = e = 0) is the class sum of the residuals
+            if (warp == 0 && qd == 0)
+                scr[kDmmaWarps * 8 + gid] = acc[0][0][0];
+        }
+        __syncthreads();
+        SQW_EPROF(5)
+
+        // ---------------- epilogue: mean / sd correction, partial gradient of this CTA ----------------
+        if (warp < kDmmaWarps && gid < P.C) {
+            const double sc = scr[kDmmaWarps * 8 + gid];
+            double *gp = P.gpart + ((size_t)blk * P.Gmax + cta) * P.npad + (size_t)gid * dimp;
+#pragma unroll
+            for (int i = 0; i < NBG; ++i) {
+                const int g = warp + kDmmaWarps * i;
+                const int col = 16 * g + 4 * qd;
+                if (g < ngroups) {
+                    const double2 s01 = __ldg(reinterpret_cast<const double2 *>(P.cinvsd + col));
+                    const double2 s23 = __ldg(reinterpret_cast<const double2 *>(P.cinvsd + col + 2));
+                    const double2 m01 = __ldg(reinterpret_cast<const double2 *>(P.cmean + col));
+                    const double2 m23 = __ldg(reinterpret_cast<const double2 *>(P.cmean + col + 2));
+                    double2 *dst = reinterpret_cast<double2 *>(gp + col);
+                    __stcg(dst, make_double2((acc[i][0][0] - m01.x * sc) * s01.x,
+                                             (acc[i][1][0] - m01.y * sc) * s01.y));
+                    __stcg(dst + 1, make_double2((acc[i][0][1] - m23.x * sc) * s23.x,
+                                                 (acc[i][1][1] - m23.y * sc) * s23.y));
+                }
+            }
+        }
+        SQW_EPROF(7)
+#undef SQW_EPROF
+        return facc;  // per-thread NLL partial
+    }
+};
+
+}  // namespace sqw

@@ -60,4 +60,14 @@ int sqw_set_device(int device)
     return SQW_OK;
 }
 
+int sqw_get_device(void)
+{
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return dev;
+}
+
 }  // extern "C"

@@ -284,8 +284,11 @@ class LOneCuda(Optimizer):
             todo.put(item)
         out: list = [None] * len(ridges)
         errors: list = []
+        parent_dev = _lib.load().sqw_get_device()   # CUDA's current device is per host thread
 
         def worker():
+            if parent_dev >= 0:
+                _lib.check(_lib.load().sqw_set_device(parent_dev))
             lo = LOneCuda(x0.copy(), smx0.copy(), self.data)
             self._clone_settings(lo)
             lo.setCtaBudget(budget)

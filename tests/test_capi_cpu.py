@@ -29,7 +29,7 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 def test_abi_version_and_kmer_sizes():
     lib = _lib.load()
-    assert lib.sqw_abi_version() == 1
+    assert lib.sqw_abi_version() == 2
     assert lib.sqw_num_kmers(4, 5) == 1280
     assert lib.sqw_num_kmers(4, 6) == 5376
     assert lib.sqw_num_kmers(4, 7) == 21760
