@@ -116,10 +116,14 @@ def build_problem(world: int):
     return d, crs, cls, w, len(des.subgroup_names)
 
 
-def make_optimizer(prep, crs, cls, w, C, T, comm=None):
+def make_optimizer(prep, crs, cls, w, C, T, comm=None, counts=None):
     from sequnwinder_b200.optimizer import LOneCuda
 
-    lo = LOneCuda(prep.x0.copy(), prep.sm_x0.copy(), prep.data)
+    if counts is not None:   # packed-count form: uint8 counts of the kept k-mers + xMean / xSD
+        lo = LOneCuda(prep.x0.copy(), prep.sm_x0.copy(), None)
+        lo.setCountMatrix(counts, prep.mean, prep.sd)
+    else:
+        lo = LOneCuda(prep.x0.copy(), prep.sm_x0.copy(), prep.data)
     lo.setRidge(RIDGE)
     lo.setADMMmaxItrs(ADMM_MAX)
     lo.setBGFSmaxItrs(-1)
@@ -276,7 +280,9 @@ def main():
     dim = prep.data.shape[1]
     nb = n_sites // T
 
-    lo = make_optimizer(prep, crs, cls, w, C, T, comm)
+    packed = os.environ.get("SQW_BENCH_FP64") is None
+    cnt8 = np.ascontiguousarray(counts[:, prep.keep]).astype(np.uint8) if packed else None
+    lo = make_optimizer(prep, crs, cls, w, C, T, comm, cnt8)
     lo.setResident(True)
 
     ev0 = torch.cuda.Event(enable_timing=True)
@@ -372,7 +378,7 @@ def main():
         t0 = time.time()
         c, hn = kc.count(my_bases, my_offs)
         t1 = time.time()
-        lo2 = make_optimizer(prep, crs, cls, w, C, T, comm)
+        lo2 = make_optimizer(prep, crs, cls, w, C, T, comm, cnt8)
         lo2._open()          # handle + problem upload (execute() would do it)
         t2 = time.time()
         lo2.execute()

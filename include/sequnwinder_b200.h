@@ -112,18 +112,25 @@ int sqw_admm_set_problem_dev(sqw_admm *h, int64_t n_rows, int32_t dim, int32_t n
  * is 8x smaller than the fp64 one, which turns the evaluation from HBM-bound into fp64-DMMA-bound
  * (DESIGN.md 2.3). Relative to the fp64 entry point the results differ by rounding only (X is never
  * rounded to fp64 element by element; the summation order differs as it does between any two
- * group sizes). Returns SQW_ERR_UNSUPPORTED when the shape is outside what the packed kernels
- * cover (then call sqw_admm_set_problem with the standardised matrix).
+ * group sizes).
  * _dev variant: the dense device count matrix of sqw_kmer_count_dev (n_rows x numK int32) plus
  * the column plan of sqw_prepare_plan_dev (keep_idx[num_kept], mean / sd indexed by ORIGINAL
- * column); dim = num_kept + 1. Counts above 255 -> SQW_ERR_UNSUPPORTED. Synchronises `stream`. */
+ * column); dim = num_kept + 1. rows_local = 0: d_counts / d_y / d_w hold all n_rows rows;
+ * rows_local = 1 (multi-GPU, sqw_admm_set_comm): they hold only the rows of this rank's blocks,
+ * i.e. the rows i < floor(n_rows / T) * T with (i mod T) mod world == rank in ascending order of i,
+ * so that every rank featurises its own sequences only (mean / sd stay the statistics of ALL rows).
+ * Shapes the packed kernels do not cover (more than 8 classes, rows longer than 768 columns, a
+ * block too large for shared memory) are expanded to the fp64 matrix on the device and run through
+ * the fp64 kernels: the call always succeeds for valid counts. Counts above 255 ->
+ * SQW_ERR_UNSUPPORTED. Synchronises `stream`. */
 int sqw_admm_set_problem_counts(sqw_admm *h, int64_t n_rows, int32_t dim, int32_t num_classes,
                                 const uint8_t *counts, const double *mean, const double *sd,
                                 const int32_t *y, const double *w);
 int sqw_admm_set_problem_counts_dev(sqw_admm *h, int64_t n_rows, int64_t numK, int32_t num_classes,
                                     const int32_t *d_counts, const int32_t *d_keep_idx,
                                     int32_t num_kept, const double *d_mean, const double *d_sd,
-                                    const int32_t *d_y, const double *d_w, void *stream);
+                                    const int32_t *d_y, const double *d_w, int32_t rows_local,
+                                    void *stream);
 
 /* setClassStructure (LOne.java:99; Classifier.java:633-736), CSR arrays with one entry per
  * design-file line in file order. Parents are meaningful for leaves only, children for

@@ -46,6 +46,12 @@ SYMBOLS = {
                                        f64p]),
     "sqw_admm_set_problem_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                            C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sqw_admm_set_problem_counts": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, u8p, f64p,
+                                              f64p, i32p, f64p]),
+    "sqw_admm_set_problem_counts_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32,
+                                                  C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                                  C.c_void_p]),
     "sqw_admm_set_structure": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, i32p, i32p, i32p,
                                          i32p, i32p, i32p, i32p]),
     "sqw_admm_set_params": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int32, C.c_int32,

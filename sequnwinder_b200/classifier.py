@@ -36,8 +36,10 @@ class Prepared:
 
 
 def prepare(counts: np.ndarray, cls: np.ndarray, weights: np.ndarray,
-            structure: ClassRelationStructure, num_classes: int) -> Prepared:
-    """Classifier.java:300-420 on a dense count matrix."""
+            structure: ClassRelationStructure, num_classes: int, materialize: bool = True) -> Prepared:
+    """Classifier.java:300-420 on a dense count matrix. ``materialize=False`` skips the
+    standardised fp64 matrix (``data`` is None): the packed-count trainer path only needs the
+    kept columns, xMean and xSD."""
     counts = np.asarray(counts)
     n = counts.shape[0]
     keep = np.nonzero(counts.max(axis=0) != counts.min(axis=0))[0]
@@ -59,7 +61,10 @@ def prepare(counts: np.ndarray, cls: np.ndarray, weights: np.ndarray,
         s = np.zeros(nR)
     mean[1:], sd[1:] = m, s
     nz = sd != 0
-    data[:, nz] = (data[:, nz] - mean[nz]) / sd[nz]
+    if materialize:
+        data[:, nz] = (data[:, nz] - mean[nz]) / sd[nz]
+    else:
+        data = None
 
     dim = nR + 1
     NN = structure.numNodes
@@ -115,13 +120,20 @@ class Classifier:
         self.optimizer: Optional[LOneCuda] = None
         self.comm = None   # (rank, world, nccl_id) for multi-GPU runs
         self.cta_budget = 0  # > 0: share of the GPU when several classifiers train side by side
+        self.use_counts = True   # train from the byte count matrix when the counts allow it
 
     def buildClassifier(self, counts: np.ndarray, cls: np.ndarray, weights: np.ndarray,
                         num_classes: int):
-        prep = prepare(counts, cls, weights, self.sm_ClassStructure, num_classes)
+        counts = np.asarray(counts)
+        # k-mer counts fit a byte (MakeArff.java:347-368: at most L - k + 1 per window length): hand
+        # the trainer the counts + xMean / xSD instead of the standardised doubles (packed-count path)
+        packed = self.use_counts and counts.size > 0 and counts.min() >= 0 and counts.max() <= 255
+        prep = prepare(counts, cls, weights, self.sm_ClassStructure, num_classes, materialize=not packed)
         self.prep = prep
         x, sm_x = prep.x0.copy(), prep.sm_x0.copy()
         opt = LOneCuda(x, sm_x, prep.data)                  # Classifier.java:424-425
+        if packed:
+            opt.setCountMatrix(counts[:, prep.keep].astype(np.uint8), prep.mean, prep.sd)
         opt.setRidge(self.m_Ridge)                          # :427
         opt.setADMMmaxItrs(self.m_ADMM_MaxIts)              # :429
         opt.setBGFSmaxItrs(self.m_BGFS_MaxIts)              # :431
@@ -130,7 +142,7 @@ class Classifier:
         opt.setClsMembership(np.asarray(cls, dtype=np.int32))  # :434
         opt.setInstanceWeights(np.asarray(weights, dtype=np.float64))  # :435
         opt.setNumClasses(num_classes)                      # :436
-        opt.setNumPredictors(prep.data.shape[1] - 1)        # :437
+        opt.setNumPredictors(prep.keep.size)                # :437
         opt.setPho(self.m_ADMM_pho)                         # :439
         opt.set_numThreads(self.m_ADMM_numThreads)          # :440
         opt.initUandZ()                                     # :441
@@ -141,7 +153,7 @@ class Classifier:
             opt.setCtaBudget(self.cta_budget)
         opt.execute()                                       # :444
         x, sm_x = opt.getX(), opt.getsmX()                  # :447-448
-        dim = prep.data.shape[1]
+        dim = prep.keep.size + 1
         self.m_Par = destandardize(x, num_classes, dim, prep.mean, prep.sd)
         self.sm_Par = destandardize(sm_x, self.sm_ClassStructure.numNodes, dim, prep.mean, prep.sd)
         self.optimizer = opt

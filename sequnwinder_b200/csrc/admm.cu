@@ -167,6 +167,7 @@ static XKernel xupdate_kernel(int nct, int mode)
     case 8 + 4: return admm_xupdate_kernel<1, 4>;
     case 8 + 6: return admm_xupdate_kernel<1, 6>;
     case 8 + 5: return admm_xupdate_kernel<1, 5>;
+    case 8 + 8: return admm_xupdate_kernel<1, 8>;
     case 8 + 1: return admm_xupdate_kernel<1, 1>;
     case 8 + 2: return admm_xupdate_kernel<1, 2>;
     case 16 + 4: return admm_xupdate_kernel<2, 4>;
@@ -187,6 +188,7 @@ static EKernel eval_kernel(int nct, int mode)
     case 8 + 4: return admm_eval_kernel<1, 4>;
     case 8 + 6: return admm_eval_kernel<1, 6>;
     case 8 + 5: return admm_eval_kernel<1, 5>;
+    case 8 + 8: return admm_eval_kernel<1, 8>;
     case 8 + 1: return admm_eval_kernel<1, 1>;
     case 8 + 2: return admm_eval_kernel<1, 2>;
     case 16 + 4: return admm_eval_kernel<2, 4>;
@@ -212,6 +214,29 @@ static int upload_ints(sqw_admm *h, const std::vector<int> &v, const int **dst)
                                        h->stream));
     *dst = p;
     return SQW_OK;
+}
+
+// CTAs per ADMM block: G while every local block is active (one CTA per SM, all T_local groups
+// co-resident) and the cap a re-grouped block may grow to in a later phase. A launch never gives
+// a block fewer than min(G, gcap) CTAs.
+static void group_sizes(const sqw_admm *h, int n_sm, int T_local, int nb, int &G, int &gcap)
+{
+    // CTA budget of this handle (sqw_admm_set_cta_budget): several handles with disjoint budgets run
+    // their cooperative x-update launches side by side on one GPU (concurrent sweep, DESIGN 2.5)
+    if (h->cta_budget > 0)
+        n_sm = std::min(n_sm, h->cta_budget);
+    G = std::max(1, n_sm / T_local);
+    const int max_useful = std::max(1, (nb + 7) / 8);
+    G = std::min(G, max_useful);
+    // measured at cfg-2 (2 500 rows per block; tools/gcap.sh): 64.5 us per evaluation round
+    // without a cap, 62.0 with 48, 63.6 with 36, 66.8 with 24. A trip costs ~ rows/G of evaluation
+    // plus ~ G of partial-gradient exchange (both scale with C * dim), so the best G grows with
+    // the square root of the block's rows: 48 at 2 500 rows, no cap in effect for large blocks.
+    // SQW_ADMM_GCAP is the tuning hook.
+    const int gcap_auto = std::max(16, (int)(0.96 * std::sqrt((double)nb) + 0.5));
+    gcap = getenv("SQW_ADMM_GCAP") ? std::max(1, atoi(getenv("SQW_ADMM_GCAP"))) : gcap_auto;
+    if (T_local == 1)
+        G = std::min(G, gcap);
 }
 
 // Allocate everything that depends on params + structure + problem sizes.
@@ -241,13 +266,11 @@ static int prepare(sqw_admm *h)
     cudaDeviceProp prop;
     SQW_CUDA_CHECK(cudaGetDeviceProperties(&prop, h->device));
     int n_sm = prop.multiProcessorCount;
-    // CTA budget of this handle (sqw_admm_set_cta_budget): several handles with disjoint budgets run
-    // their cooperative x-update launches side by side on one GPU (concurrent sweep, DESIGN 2.5)
     if (h->cta_budget > 0)
         n_sm = std::min(n_sm, h->cta_budget);
     const int mode = h->eval_mode;
     const size_t w_bytes = (size_t)D.Cp * D.wstride * sizeof(double);
-    if (mode == 4 || mode == 5 || mode == 6)
+    if (mode == 4 || mode == 5 || mode == 6 || mode == 8)
         h->xupdate_smem = h->layout.total;
     else if (mode == 1)
         h->xupdate_smem = w_bytes;
@@ -274,27 +297,14 @@ static int prepare(sqw_admm *h)
     if (per_sm < 1)
         return set_error(SQW_ERR_UNSUPPORTED, "x-update kernel does not fit on an SM");
     // one CTA per SM: G CTAs per ADMM block, all T_local groups co-resident
-    int G = n_sm / D.T_local;
-    if (G < 1) {
-        G = 1;
-        if (D.T_local > n_sm * per_sm)
-            return set_error(SQW_ERR_UNSUPPORTED, "%d local ADMM blocks exceed %d co-resident CTAs",
-                             D.T_local, n_sm * per_sm);
-    }
-    const int max_useful = std::max(1, (D.nb + 7) / 8);
-    G = std::min(G, max_useful);
+    if (D.T_local > n_sm * per_sm)
+        return set_error(SQW_ERR_UNSUPPORTED, "%d local ADMM blocks exceed %d co-resident CTAs",
+                         D.T_local, n_sm * per_sm);
+    int G = 1;
+    group_sizes(h, prop.multiProcessorCount, D.T_local, D.nb, G, D.gcap);
     // a rank that owns a single block has nothing to re-group: one launch, run to completion
     h->nphase = (D.T_local == 1) ? 1 : kNumPhases;
     D.nphase = h->nphase;
-    // measured at cfg-2 (2 500 rows per block; tools/gcap.sh): 64.5 us per evaluation round
-    // without a cap, 62.0 with 48, 63.6 with 36, 66.8 with 24. A trip costs ~ rows/G of evaluation
-    // plus ~ G of partial-gradient exchange (both scale with C * dim), so the best G grows with
-    // the square root of the block's rows: 48 at 2 500 rows, no cap in effect for large blocks.
-    // SQW_ADMM_GCAP is the tuning hook.
-    const int gcap_auto = std::max(16, (int)(0.96 * std::sqrt((double)D.nb) + 0.5));
-    D.gcap = getenv("SQW_ADMM_GCAP") ? std::max(1, atoi(getenv("SQW_ADMM_GCAP"))) : gcap_auto;
-    if (D.T_local == 1)
-        G = std::min(G, D.gcap);
     D.G = G;
     D.Gmax = G * D.T_local;
 
@@ -359,7 +369,7 @@ static int prepare(sqw_admm *h)
     // cfg-2), but pinning part of it made no measurable difference to the x-update, and the
     // carve-out is a device-wide setting that slows other kernels (the k-mer pass ran 4x slower
     // next to a resident trainer), so it is off unless asked for.
-    if (const char *env = getenv("SQW_ADMM_L2_PERSIST_MB")) {
+    if (const char *env = D.X ? getenv("SQW_ADMM_L2_PERSIST_MB") : nullptr) {
         const size_t x_bytes = (size_t)D.T_local * D.nb * D.dimp * sizeof(double);
         size_t persist = std::min((size_t)prop.persistingL2CacheMaxSize, (size_t)atol(env) << 20);
         if (persist > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist) == cudaSuccess) {
@@ -541,7 +551,7 @@ int sqw_admm_set_cta_budget(sqw_admm *h, int32_t max_ctas)
         return set_error(SQW_ERR_INVALID_ARG, "null handle");
     if (max_ctas < 0)
         return set_error(SQW_ERR_INVALID_ARG, "negative CTA budget");
-    if (h->dev.X)
+    if (h->have_problem)
         return set_error(SQW_ERR_INVALID_ARG, "set the CTA budget before sqw_admm_set_problem");
     h->cta_budget = max_ctas;
     return SQW_OK;
@@ -705,7 +715,8 @@ int sqw_admm_set_comm(sqw_admm *h, int32_t rank, int32_t world, const uint8_t nc
 // Row blocking shared by both set_problem variants (LOne.java:337-357): block t holds rows
 // i = t + T*s, s < floor(N/T); the local blocks are those with t % world == rank, stored in the
 // order the reference sums the thread buffers.
-static int plan_blocks(sqw_admm *h, int64_t n_rows, int32_t dim, int32_t num_classes)
+static int plan_blocks(sqw_admm *h, int64_t n_rows, int32_t dim, int32_t num_classes,
+                       bool counts_form = false)
 {
     if (!h || n_rows < 1 || dim < 2 || num_classes < 1)
         return set_error(SQW_ERR_INVALID_ARG, "invalid problem sizes");
@@ -774,6 +785,25 @@ static int plan_blocks(sqw_admm *h, int64_t n_rows, int32_t dim, int32_t num_cla
     h->eval_mode = mode;
     h->layout = (mode == 6) ? Lc : L;
     D.dimp = (mode == 4 || mode == 5 || mode == 6) ? dimp4 : dimp8;
+    // Packed-count form (admm_eval_packed.cuh): one class tile, rows up to 768 columns, and the
+    // rows of the busiest CTA of the smallest group a launch can form must fit shared memory next
+    // to the partial logits. Otherwise the counts are expanded to the fp64 matrix on the device.
+    if (counts_form && nct == 1 && dim <= kPackedMaxDim && !getenv("SQW_ADMM_NO_PACKED") &&
+        !getenv("SQW_ADMM_EVAL_MODE")) {
+        const int dimp16 = (dim + 15) / 16 * 16;
+        int G = 1, gcap = 1;
+        group_sizes(h, prop.multiProcessorCount, D.T_local, D.nb, G, gcap);
+        const int gmin = std::min(G, gcap);
+        const long long tiles = (D.nb + 7) / 8;
+        const int rows_cap8 = (int)((tiles + gmin - 1) / gmin) * 8;
+        TileSmemLayout Lp = packed_smem_layout(dimp16, rows_cap8, kSolveSliceBytes);
+        if (Lp.total <= budget) {
+            h->eval_mode = 8;
+            h->layout = Lp;
+            D.dimp = dimp16;
+            D.rsq = dimp16;
+        }
+    }
     return SQW_OK;
 }
 
@@ -867,6 +897,124 @@ int sqw_admm_set_problem_dev(sqw_admm *h, int64_t n_rows, int32_t dim, int32_t n
     D.w = dw;
     h->have_problem = true;
     return SQW_OK;
+}
+
+}  // extern "C"
+
+// Shared tail of the two count-matrix entry points: d_src holds the counts on the device
+// (SrcT = uint8 with the kept features as consecutive columns, or int32 with a column index list).
+template <typename SrcT>
+static int build_from_counts(sqw_admm *h, const SrcT *d_src, long long src_stride, const int *d_col_idx,
+                             const double *d_mean, const double *d_sd, const int *d_y,
+                             const double *d_w, int rows_local, cudaStream_t st)
+{
+    AdmmDev &D = h->dev;
+    int rc;
+    const size_t rows = (size_t)D.T_local * D.nb;
+    double *dw = nullptr, *mean_p = nullptr, *invsd_p = nullptr, *mean_f = nullptr, *sd_f = nullptr;
+    int *dy = nullptr, *dbid = nullptr, *dstatus = nullptr;
+    if ((rc = h->dalloc(&dy, rows, false)) != SQW_OK) return rc;
+    if ((rc = h->dalloc(&dw, rows, false)) != SQW_OK) return rc;
+    if ((rc = h->dalloc(&dbid, (size_t)D.T_local, false)) != SQW_OK) return rc;
+    if ((rc = h->dalloc(&dstatus, 1, true)) != SQW_OK) return rc;
+    if ((rc = h->dalloc(&mean_p, (size_t)D.dimp, false)) != SQW_OK) return rc;
+    if ((rc = h->dalloc(&invsd_p, (size_t)D.dimp, false)) != SQW_OK) return rc;
+    if ((rc = h->dalloc(&mean_f, (size_t)D.dimp, false)) != SQW_OK) return rc;
+    if ((rc = h->dalloc(&sd_f, (size_t)D.dimp, false)) != SQW_OK) return rc;
+    // (allocation and memset ran on the handle's stream: order the caller's stream behind them)
+    SQW_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    SQW_CUDA_CHECK(cudaMemcpyAsync(dbid, h->block_ids.data(), sizeof(int) * D.T_local,
+                                   cudaMemcpyHostToDevice, st));
+    admm_packed_stats_kernel<<<(D.dimp + 255) / 256, 256, 0, st>>>(d_mean, d_sd, d_col_idx, D.dim, D.dimp,
+                                                                   mean_p, invsd_p, mean_f, sd_f);
+    const int grid = (int)std::min<size_t>(rows, 148 * 16);
+    if (h->eval_mode == 8) {
+        unsigned char *dXq = nullptr;
+        if ((rc = h->dalloc(&dXq, rows * D.rsq + 16384, false)) != SQW_OK) return rc;
+        admm_gather_counts_kernel<SrcT, true><<<grid, 256, 0, st>>>(
+            d_src, src_stride, d_col_idx, d_y, d_w, D.dim, h->T, dbid, D.T_local, D.nb, h->world,
+            rows_local, mean_f, sd_f, D.rsq, dXq, dy, dw, dstatus);
+        D.Xq = dXq;
+        D.cmean = mean_p;
+        D.cinvsd = invsd_p;
+    } else {
+        double *dX = nullptr;
+        if ((rc = h->dalloc(&dX, rows * D.dimp, false)) != SQW_OK) return rc;
+        admm_gather_counts_kernel<SrcT, false><<<grid, 256, 0, st>>>(
+            d_src, src_stride, d_col_idx, d_y, d_w, D.dim, h->T, dbid, D.T_local, D.nb, h->world,
+            rows_local, mean_f, sd_f, D.dimp, dX, dy, dw, dstatus);
+        D.X = dX;
+    }
+    SQW_CUDA_CHECK(cudaGetLastError());
+    int status = 0;
+    SQW_CUDA_CHECK(cudaMemcpyAsync(&status, dstatus, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SQW_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (status != 0)
+        return set_error(SQW_ERR_UNSUPPORTED, "a count exceeds 255: pass the standardised matrix to "
+                                              "sqw_admm_set_problem instead");
+    D.y = dy;
+    D.w = dw;
+    h->have_problem = true;
+    return SQW_OK;
+}
+
+extern "C" {
+
+int sqw_admm_set_problem_counts(sqw_admm *h, int64_t n_rows, int32_t dim, int32_t num_classes,
+                                const uint8_t *counts, const double *mean, const double *sd,
+                                const int32_t *y, const double *w)
+{
+    int rc = plan_blocks(h, n_rows, dim, num_classes, true);
+    if (rc != SQW_OK)
+        return rc;
+    if (!counts || !mean || !sd || !y || !w)
+        return set_error(SQW_ERR_INVALID_ARG, "null buffer");
+    for (int64_t i = 0; i < n_rows; ++i)
+        if (y[i] < 0 || y[i] >= num_classes)
+            return set_error(SQW_ERR_INVALID_ARG, "class %d of row %lld out of range", y[i], (long long)i);
+    SQW_CUDA_CHECK(cudaSetDevice(h->device));
+    // the whole count matrix is 1 byte per element (13 MB at cfg-2): one copy, then the same device
+    // gather as the _dev variant; the scratch copies are freed before returning
+    const size_t F = (size_t)dim - 1;
+    uint8_t *d_src = nullptr;
+    double *d_ms = nullptr, *d_w = nullptr;
+    int *d_y = nullptr;
+    cudaError_t e = cudaMalloc((void **)&d_src, (size_t)n_rows * F);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_ms, sizeof(double) * 2 * dim);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_w, sizeof(double) * n_rows);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_y, sizeof(int) * n_rows);
+    cudaStream_t st = h->stream;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_src, counts, (size_t)n_rows * F, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_ms, mean, sizeof(double) * dim, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_ms + dim, sd, sizeof(double) * dim, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_w, w, sizeof(double) * n_rows, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_y, y, sizeof(int) * n_rows, cudaMemcpyHostToDevice, st);
+    rc = (e == cudaSuccess) ? build_from_counts<uint8_t>(h, d_src, (long long)F, nullptr, d_ms, d_ms + dim,
+                                                          d_y, d_w, 0, st)
+                            : set_error(SQW_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e));
+    cudaFree(d_src);
+    cudaFree(d_ms);
+    cudaFree(d_w);
+    cudaFree(d_y);
+    return rc;
+}
+
+int sqw_admm_set_problem_counts_dev(sqw_admm *h, int64_t n_rows, int64_t numK, int32_t num_classes,
+                                    const int32_t *d_counts, const int32_t *d_keep_idx,
+                                    int32_t num_kept, const double *d_mean, const double *d_sd,
+                                    const int32_t *d_y, const double *d_w, int32_t rows_local,
+                                    void *stream)
+{
+    if (num_kept < 1 || numK < num_kept)
+        return set_error(SQW_ERR_INVALID_ARG, "invalid column plan");
+    int rc = plan_blocks(h, n_rows, num_kept + 1, num_classes, true);
+    if (rc != SQW_OK)
+        return rc;
+    if (!d_counts || !d_keep_idx || !d_mean || !d_sd || !d_y || !d_w)
+        return set_error(SQW_ERR_INVALID_ARG, "null buffer");
+    SQW_CUDA_CHECK(cudaSetDevice(h->device));
+    return build_from_counts<int32_t>(h, d_counts, (long long)numK, d_keep_idx, d_mean, d_sd, d_y, d_w,
+                                      rows_local ? 1 : 0, (cudaStream_t)stream);
 }
 
 // host <-> padded device layout helpers

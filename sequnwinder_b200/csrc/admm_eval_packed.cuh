@@ -16,10 +16,10 @@
 // All arithmetic is fp64; counts convert exactly. The products are the same DMMA m8n8k4 passes as
 // the fp64 modes, but nothing crosses HBM after the launch prologue and nothing waits on a tile:
 //
-//   pass 1   all tiles: partial logits per DMMA warp (K split over the 8 warps by 16-column groups:
-//            one LDS.32 = 4 k-steps of one row) -> shared memory
+//   pass 1   partial logits per DMMA warp (K split over the 8 warps by 16-column groups: one LDS.32
+//            = 4 k-steps of one row) -> shared memory
 //   softmax  all 11 warps: sum of the 8 K-slices, max-shifted softmax, residuals R, NLL
-//   pass 2   all tiles: G += R^T n with the accumulators in registers (one LDS.U16 = 2 columns)
+//   pass 2   G += R^T n with the accumulators in registers (one LDS.U16 = 2 columns)
 //   epilogue the mean / sd correction of the CTA's partial gradient, one store
 //
 // three __syncthreads per evaluation instead of two named-barrier hand-offs per 8-row tile.
@@ -57,15 +57,27 @@ inline TileSmemLayout packed_smem_layout(int rsq, int rows_cap8, size_t slice_by
     L.stage_bytes = ((size_t)rows_cap8 * rsq + 127) & ~(size_t)127;
     L.plog_off = L.stage_off + L.stage_bytes;
     L.rs_off = L.plog_off + (size_t)kDmmaWarps * rows_cap8 * 8 * sizeof(double);
-    L.bar_off = L.rs_off + (kDmmaWarps * 8 + 8) * sizeof(double);
+    // scratch: 8 x 8 offset partials + 8 class sums | xMean, 1/xSD [rsq each] | w [rows], y [rows]
+    L.bar_off = L.rs_off + (size_t)(kDmmaWarps * 8 + 8 + 2 * rsq + rows_cap8) * sizeof(double) +
+                (((size_t)rows_cap8 * sizeof(int) + 15) & ~(size_t)15);
     L.total = L.bar_off + 128;
     L.NS = rows_cap8 / kTileRows;  // tiles the resident buffer holds
     return L;
 }
 
+#ifndef SQW_PACKED_CVT_MAGIC
+#define SQW_PACKED_CVT_MAGIC 0
+#endif
+// exact conversion of a byte. I2F.F64 runs beside the DMMAs; the alternative (2^52 + v built with one
+// integer op, the 2^52 removed by a DADD) was measured slower at cfg-2 (55.7 vs 52.3 us per
+// evaluation round): the DADD shares the fp64 pipe with DMMA
 __device__ __forceinline__ double cvt_u8(unsigned v)
 {
+#if SQW_PACKED_CVT_MAGIC
+    return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
+#else
     return __uint2double_rn(v);
+#endif
 }
 
 template <int NCT>
@@ -75,7 +87,8 @@ struct PackedEval {
     const AdmmDev &P;
     int blk, cta, G;
     unsigned char *rows;
-    double *plog, *scr;
+    double *plog, *scr, *smean, *sinvsd, *sw;
+    int *sy;
     unsigned long long *full;
     double *red;
     int cap8, r0, r1, ntiles, rsq;
@@ -91,10 +104,24 @@ struct PackedEval {
         red = red_;
         cap8 = L.NS * kTileRows;
         rsq = P.rsq;
+        smean = scr + kDmmaWarps * 8 + 8;
+        sinvsd = smean + rsq;
+        sw = sinvsd + rsq;
+        sy = reinterpret_cast<int *>(sw + cap8);
         cta_row_range(P, cta, G, r0, r1);
         ntiles = max(0, (r1 - r0 + kTileRows - 1) / kTileRows);
         loaded = false;
         prof = nullptr;
+        // constant for the launch: the column statistics and this CTA's instance weights / classes
+        for (int i = threadIdx.x; i < rsq; i += kThreads) {
+            smean[i] = __ldg(P.cmean + i);
+            sinvsd[i] = __ldg(P.cinvsd + i);
+        }
+        for (int i = threadIdx.x; i < ntiles * kTileRows; i += kThreads) {
+            const bool rv = r0 + i < r1;
+            sw[i] = rv ? __ldg(P.w + (size_t)blk * P.nb + r0 + i) : 0.0;
+            sy[i] = rv ? __ldg(P.y + (size_t)blk * P.nb + r0 + i) : -1;
+        }
         if (threadIdx.x == 0) {
             mbar_init(&full[0], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -136,9 +163,14 @@ struct PackedEval {
         tk0 = tk1;               \
     }
         double *rres = plog;  // residuals overwrite K-slice 0 of the partial logits, row by row
+        const bool dmma_warp = warp < kDmmaWarps;
+        // (Splitting the tiles into two halves so that the three warps that issue no DMMA compute the
+        // softmax of one half while the DMMA warps work on the other was measured SLOWER - 61.3 vs
+        // 52.1 us per evaluation round at cfg-2: exp / div / log are DFMA chains on the same fp64 pipe
+        // the DMMAs saturate, so there is nothing to overlap with.)
 
         // ---------------- pass 1: partial logits of every tile ----------------
-        if (warp < kDmmaWarps) {
+        if (dmma_warp) {
             // V[class gid][16 g + 4 qd + t] = W / sd for this warp's column groups, and the warp's
             // part of the offset o[class] = sum_j mean[j] V[class][j]
             double wreg[NBG * 4];
@@ -149,10 +181,10 @@ struct PackedEval {
                 const int col = 16 * g + 4 * qd;
                 double2 w01 = make_double2(0.0, 0.0), w23 = w01, s01 = w01, s23 = w01, m01 = w01, m23 = w01;
                 if (g < ngroups) {
-                    s01 = __ldg(reinterpret_cast<const double2 *>(P.cinvsd + col));
-                    s23 = __ldg(reinterpret_cast<const double2 *>(P.cinvsd + col + 2));
-                    m01 = __ldg(reinterpret_cast<const double2 *>(P.cmean + col));
-                    m23 = __ldg(reinterpret_cast<const double2 *>(P.cmean + col + 2));
+                    s01 = *reinterpret_cast<const double2 *>(sinvsd + col);
+                    s23 = *reinterpret_cast<const double2 *>(sinvsd + col + 2);
+                    m01 = *reinterpret_cast<const double2 *>(smean + col);
+                    m23 = *reinterpret_cast<const double2 *>(smean + col + 2);
                     if (gid < P.C) {
                         const double *wg = xcur + (size_t)gid * dimp + col;
                         w01 = __ldcg(reinterpret_cast<const double2 *>(wg));
@@ -209,7 +241,7 @@ struct PackedEval {
         __syncthreads();
         SQW_EPROF(2)
 
-        // ---------------- softmax of every row: residuals, NLL ----------------
+        // ---------------- softmax of every row (all 11 warps): residuals, NLL ----------------
         double facc = 0.0;
         {
             double o0 = 0.0, o1 = 0.0;
@@ -218,15 +250,12 @@ struct PackedEval {
                 o0 += scr[w8 * 8 + 2 * qd];
                 o1 += scr[w8 * 8 + 2 * qd + 1];
             }
-            const int *yb = P.y + (size_t)blk * P.nb;
-            const double *wb = P.w + (size_t)blk * P.nb;
+#pragma unroll 2
             for (int j = warp; j < ntiles; j += kWarps) {
                 const int lr = kTileRows * j + gid;
-                const int row = r0 + lr;
-                const bool rv = row < r1;
-                const int rowc = rv ? row : r0;
-                const int cls = yb[rowc];
-                const double wi = wb[rowc];
+                const bool rv = r0 + lr < r1;
+                const int cls = sy[lr];      // -1 and weight 0 beyond the CTA's last row
+                const double wi = sw[lr];
                 double2 v = *reinterpret_cast<const double2 *>(plog + (size_t)lr * 8 + 2 * qd);
 #pragma unroll
                 for (int w8 = 1; w8 < kDmmaWarps; ++w8) {
@@ -273,7 +302,7 @@ struct PackedEval {
 #pragma unroll
             for (int h = 0; h < 2; ++h)
                 acc[i][h][0] = acc[i][h][1] = 0.0;
-        if (warp < kDmmaWarps) {
+        if (dmma_warp) {
             const bool last_group = warp + kDmmaWarps * (NBG - 1) < ngroups;
 #pragma unroll 2
             for (int j = 0; j < ntiles; ++j) {
@@ -288,12 +317,19 @@ struct PackedEval {
                     x0[i] = (g < ngroups) ? *reinterpret_cast<const unsigned short *>(rp0 + 16 * g) : 0u;
                     x1[i] = (g < ngroups) ? *reinterpret_cast<const unsigned short *>(rp1 + 16 * g) : 0u;
                 }
+                // rows 0..3 of every group first, then rows 4..7: an accumulator is re-used at a
+                // distance of 2 NBG DMMAs (latency 26 cycles, issue 16)
 #pragma unroll
                 for (int i = 0; i < NBG; ++i) {
                     if (i == NBG - 1 && !last_group)
                         break;
                     dmma884(acc[i][0], a0, cvt_u8(x0[i] & 0xffu));
                     dmma884(acc[i][1], a0, cvt_u8(x0[i] >> 8));
+                }
+#pragma unroll
+                for (int i = 0; i < NBG; ++i) {
+                    if (i == NBG - 1 && !last_group)
+                        break;
                     dmma884(acc[i][0], a1, cvt_u8(x1[i] & 0xffu));
                     dmma884(acc[i][1], a1, cvt_u8(x1[i] >> 8));
                 }
@@ -315,10 +351,10 @@ struct PackedEval {
                 const int g = warp + kDmmaWarps * i;
                 const int col = 16 * g + 4 * qd;
                 if (g < ngroups) {
-                    const double2 s01 = __ldg(reinterpret_cast<const double2 *>(P.cinvsd + col));
-                    const double2 s23 = __ldg(reinterpret_cast<const double2 *>(P.cinvsd + col + 2));
-                    const double2 m01 = __ldg(reinterpret_cast<const double2 *>(P.cmean + col));
-                    const double2 m23 = __ldg(reinterpret_cast<const double2 *>(P.cmean + col + 2));
+                    const double2 s01 = *reinterpret_cast<const double2 *>(sinvsd + col);
+                    const double2 s23 = *reinterpret_cast<const double2 *>(sinvsd + col + 2);
+                    const double2 m01 = *reinterpret_cast<const double2 *>(smean + col);
+                    const double2 m23 = *reinterpret_cast<const double2 *>(smean + col + 2);
                     double2 *dst = reinterpret_cast<double2 *>(gp + col);
                     __stcg(dst, make_double2((acc[i][0][0] - m01.x * sc) * s01.x,
                                              (acc[i][1][0] - m01.y * sc) * s01.y));

@@ -22,6 +22,7 @@
 #pragma once
 
 #include "admm_eval_tma.cuh"
+#include "admm_eval_packed.cuh"
 #include "admm_solver.cuh"
 
 namespace sqw {
@@ -38,6 +39,8 @@ __device__ __forceinline__ int ld_volatile_int(const int *p)
 //   MODE 6  two passes over column-chunked TMA-staged tiles (TileEvalChunk): any row length;
 //   MODE 1  two streaming passes from global memory, W in shared memory (admm_eval.cuh);
 //   MODE 2  the same with W read from global memory (row lengths beyond shared memory).
+//   MODE 8  the CTA's rows as byte counts resident in shared memory, three bulk phases per
+//           evaluation (PackedEval): count matrices with rows up to 768 columns and C <= 8.
 template <int NCT, int MODE>
 struct StreamEval {
     const AdmmDev &P;
@@ -71,6 +74,10 @@ struct EvalSelect<NCT, 6> {   // column-chunked TMA tiles: any row length
 template <int NCT>
 struct EvalSelect<NCT, 5> {   // MODE 4 with 21 k-steps per DMMA warp (rows <= 672 columns)
     typedef TileEvalWS<NCT, 21> type;
+};
+template <int NCT>
+struct EvalSelect<NCT, 8> {   // packed counts resident in shared memory (admm_eval_packed.cuh)
+    typedef PackedEval<NCT> type;
 };
 
 // Shared-memory copy of the (tiny) leaf -> edge -> parent tables: the augmented term of every
@@ -338,7 +345,8 @@ admm_xupdate_kernel(AdmmDev P, TileSmemLayout L, int phase, int eval_cap)
     ws.cta = cta;
     ws.prof = P.prof ? s_prof : nullptr;
     // modes 4/5 keep W in registers: the head of the dynamic shared memory is the slice cache
-    ws.slice = ((MODE == 4 || MODE == 5) && NCT == 1) ? reinterpret_cast<double *>(smem_raw) : nullptr;
+    ws.slice = ((MODE == 4 || MODE == 5 || MODE == 8) && NCT == 1) ? reinterpret_cast<double *>(smem_raw)
+                                                                  : nullptr;
     int status = 0;
     bool finished = false;
     const long long t_loop0 = (P.prof && threadIdx.x == 0) ? sqw_now_ns() : 0;
@@ -750,6 +758,81 @@ admm_block_rows_kernel(const double *src, const int *ysrc, const double *wsrc, i
     }
 }
 
+// The same gather from a COUNT matrix (MakeArff.java:347-368 rows before Classifier.java:373-381):
+// src row i holds the counts of the features (column col_idx[j-1] when col_idx is given, else
+// j-1) for j = 1..dim-1; destination column 0 is the constant 1 (Classifier.java:340).
+//   PACKED   bytes, row stride `stride` (MODE 8); a count above 255 raises status bit 0
+//   !PACKED  fp64 (n - mean[j]) / sd[j] where sd[j] != 0 (Classifier.java:373-381), row stride `stride`
+// rows_local: src / ysrc / wsrc hold only this rank's rows in ascending global order, i.e. local
+// row s * T_local + t / world for block t (the rank owns the blocks t = rank mod world).
+template <typename SrcT, bool PACKED>
+__global__ void __launch_bounds__(256)
+admm_gather_counts_kernel(const SrcT *src, long long src_stride, const int *col_idx, const int *ysrc,
+                          const double *wsrc, int dim, int T, const int *block_ids, int T_local,
+                          int nb, int world, int rows_local, const double *mean, const double *sd,
+                          int stride, void *Xout, int *y, double *w, int *status)
+{
+    const long long rows = (long long)T_local * nb;
+    for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+        const int b = (int)(r / nb), s = (int)(r - (long long)b * nb);
+        const int t = block_ids[b];
+        const long long i = rows_local ? (long long)s * T_local + t / world : (long long)t + (long long)T * s;
+        const SrcT *in = src + i * src_stride;
+        for (int j = threadIdx.x; j < stride; j += blockDim.x) {
+            long long v = 0;
+            if (j == 0)
+                v = 1;
+            else if (j < dim)
+                v = (long long)in[col_idx ? col_idx[j - 1] : j - 1];
+            if (PACKED) {
+                if (v < 0 || v > 255) {
+                    atomicOr(status, 1);
+                    v = 0;
+                }
+                static_cast<unsigned char *>(Xout)[r * stride + j] = (unsigned char)v;
+            } else {
+                double x = (double)v;
+                if (j >= 1 && j < dim && sd[j] != 0.0)
+                    x = (x - mean[j]) / sd[j];
+                static_cast<double *>(Xout)[r * stride + j] = x;
+            }
+        }
+        if (threadIdx.x == 0) {
+            y[r] = ysrc[i];
+            w[r] = wsrc[i];
+        }
+    }
+}
+
+// mean_p / invsd_p [dimp] of the packed form from xMean / xSD: per feature j (src index
+// col_idx[j-1] + ... when the statistics are indexed by original column, else j)
+__global__ void __launch_bounds__(256)
+admm_packed_stats_kernel(const double *mean, const double *sd, const int *col_idx, int dim, int dimp,
+                         double *mean_p, double *invsd_p, double *mean_f, double *sd_f)
+{
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < dimp; j += gridDim.x * blockDim.x) {
+        double m = 0.0, s = 0.0, is = 0.0;
+        if (j == 0) {
+            s = 1.0;
+            is = 1.0;
+        } else if (j < dim) {
+            const int k = col_idx ? col_idx[j - 1] : j;
+            m = mean[k];
+            s = sd[k];
+            if (s != 0.0) {
+                is = 1.0 / s;
+            } else {  // Classifier.java:376: a column with zero SD keeps its raw values
+                m = 0.0;
+                is = 1.0;
+            }
+        }
+        mean_p[j] = m;
+        invsd_p[j] = is;
+        mean_f[j] = (j >= 1 && j < dim) ? mean[col_idx ? col_idx[j - 1] : j] : 0.0;
+        sd_f[j] = (j >= 1 && j < dim) ? s : (j == 0 ? 1.0 : 0.0);
+    }
+}
+
 // ------------------------------------------------------------------ test kernels
 // One evaluation per local block at the current x_t with the device's z / u_t / sm_x state.
 template <int NCT, int MODE>
@@ -767,7 +850,7 @@ admm_eval_kernel(AdmmDev P, TileSmemLayout L, double pho, double *f_out)
     BlockProblem<Eval> prob{P, blk, cta, P.G, pho, P.ut + (size_t)blk * P.upad, ev,
                             P.leaf_edge_ptr, P.edge_par};
     double fpart = prob.eval_partial(xt);
-    if (MODE == 4 || MODE == 5 || MODE == 6) {
+    if (MODE == 4 || MODE == 5 || MODE == 6 || MODE == 8) {
         // further evaluations exercise the ring wrap-around / resident path; results must agree
         for (int rep = 0; rep < 2; ++rep) {
             __syncthreads();

@@ -78,6 +78,12 @@ struct AdmmDev {
     const int *y;      // [T_local][nb]
     const double *w;   // [T_local][nb]
     const int *block_ids;  // [T_local] global block index t of each local block
+    // packed-count form of the same matrix (MODE 8, admm_eval_packed.cuh): counts as bytes with
+    // column 0 == 1, and the column statistics that turn them into X = (n - mean) / sd
+    const unsigned char *Xq;  // [T_local][nb][rsq]
+    int rsq;                  // row stride in bytes (= dimp, a multiple of 16)
+    const double *cmean;      // [dimp]  xMean (0 for the intercept, padding and sd == 0 columns)
+    const double *cinvsd;     // [dimp]  1 / xSD (1 for the intercept and sd == 0 columns, 0 for padding)
 
     // ---- label hierarchy ----
     const int *edge_leaf;     // [E]

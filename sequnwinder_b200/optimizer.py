@@ -112,6 +112,26 @@ class LOneCuda(Optimizer):
         self.stats: Optional[_lib.AdmmStats] = None
         self.log: Optional[AdmmLog] = None
         self._local_blocks = 0
+        self._counts = None       # (uint8 counts [n, dim-1], xMean [dim], xSD [dim]): packed-count form
+        self._counts_dev = None   # (cuda int32 counts, keep_idx, mean, sd, y, w, rows_local)
+
+    def setCountMatrix(self, counts: np.ndarray, mean: np.ndarray, sd: np.ndarray):
+        """The training matrix as the k-mer COUNTS it was standardised from (uint8 n x (dim-1), the
+        features in column order) plus xMean / xSD (dim entries, entry 0 = 0 / 1,
+        Classifier.java:362-371). execute() then goes through ``sqw_admm_set_problem_counts``: the
+        trainer evaluates on X = (counts - xMean) / xSD without materialising it (packed-count
+        kernels; shapes they do not cover are expanded to fp64 on the device). ``data`` may be None."""
+        counts = np.ascontiguousarray(counts, dtype=np.uint8)
+        self._counts = (counts, np.ascontiguousarray(mean, dtype=np.float64),
+                        np.ascontiguousarray(sd, dtype=np.float64))
+
+    def setCountMatrixDevice(self, counts, keep_idx, mean, sd, y, w, n_rows: int, rows_local: bool = False):
+        """Device-resident form (cuda tensors): the dense int32 count matrix of
+        ``KmerCounter.count_device`` [rows, numK], the column plan of ``prepare_device``
+        (keep_idx int32 [F], mean / sd fp64 [numK] by ORIGINAL column), class ids int32 and weights
+        fp64 per row. ``n_rows`` is the global row count; with ``rows_local`` the tensors hold only
+        this rank's rows (see include/sequnwinder_b200.h)."""
+        self._counts_dev = (counts, keep_idx, mean, sd, y, w, int(n_rows), bool(rows_local))
 
     # ---- setters, LOne.java:92-104 ----
     def setBGFSmaxItrs(self, m): self.BGFS_maxIts = int(m)
@@ -162,8 +182,14 @@ class LOneCuda(Optimizer):
         lib = _lib.load()
         if self.classStructure is None or self.cls is None or self.weights is None:
             raise RuntimeError("setClassStructure / setClsMembership / setInstanceWeights first")
-        data = np.ascontiguousarray(self.data, dtype=np.float64)
-        n_rows, dim = data.shape
+        data = None
+        if self._counts_dev is not None:
+            n_rows, dim = self._counts_dev[6], int(self._counts_dev[1].numel()) + 1
+        elif self._counts is not None:
+            n_rows, dim = self._counts[0].shape[0], self._counts[0].shape[1] + 1
+        else:
+            data = np.ascontiguousarray(self.data, dtype=np.float64)
+            n_rows, dim = data.shape
         C_ = self.numClasses if self.numClasses is not None else int(np.max(self.cls)) + 1
         if self.numPredictors is not None and self.numPredictors + 1 != dim:
             raise ValueError("data has %d columns but numPredictors+1 = %d"
@@ -198,13 +224,31 @@ class LOneCuda(Optimizer):
             if self._world > 1:
                 idbuf = (C.c_uint8 * 128).from_buffer_copy(self._nccl_id)
                 _lib.check(lib.sqw_admm_set_comm(h, self._rank, self._world, idbuf))
-            _lib.check(lib.sqw_admm_set_problem(
-                h, n_rows, dim, C_, data.ctypes.data_as(_lib.f64p), cls.ctypes.data_as(_lib.i32p),
-                w.ctypes.data_as(_lib.f64p)))
+            if self._counts_dev is not None:
+                import torch
+                cd, keep, mean, sd, yd, wd, _, local = self._counts_dev
+                stream = C.c_void_p(torch.cuda.current_stream(cd.device).cuda_stream)
+                _lib.check(lib.sqw_admm_set_problem_counts_dev(
+                    h, n_rows, cd.shape[1], C_, cd.data_ptr(), keep.data_ptr(), int(keep.numel()),
+                    mean.data_ptr(), sd.data_ptr(), yd.data_ptr(), wd.data_ptr(), int(local), stream))
+                self.h2d_bytes = 0
+            elif self._counts is not None:
+                cnt, mean, sd = self._counts
+                if mean.size != dim or sd.size != dim or cls.size != n_rows or w.size != n_rows:
+                    raise ValueError("count matrix / statistics / labels disagree in size")
+                _lib.check(lib.sqw_admm_set_problem_counts(
+                    h, n_rows, dim, C_, cnt.ctypes.data_as(_lib.u8p), mean.ctypes.data_as(_lib.f64p),
+                    sd.ctypes.data_as(_lib.f64p), cls.ctypes.data_as(_lib.i32p),
+                    w.ctypes.data_as(_lib.f64p)))
+                self.h2d_bytes = cnt.nbytes + mean.nbytes + sd.nbytes + cls.nbytes + w.nbytes
+            else:
+                _lib.check(lib.sqw_admm_set_problem(
+                    h, n_rows, dim, C_, data.ctypes.data_as(_lib.f64p), cls.ctypes.data_as(_lib.i32p),
+                    w.ctypes.data_as(_lib.f64p)))
+                self.h2d_bytes = data.nbytes + cls.nbytes + w.nbytes
         except Exception:
             self.close()
             raise
-        self.h2d_bytes = data.nbytes + cls.nbytes + w.nbytes
 
     def execute(self):
         lib = _lib.load()
@@ -258,6 +302,7 @@ class LOneCuda(Optimizer):
                                                                  self.numNodes)
         other.classStructure, other.weights, other.cls = self.classStructure, self.weights, self.cls
         other.sm_Debug = self.sm_Debug
+        other._counts, other._counts_dev = self._counts, self._counts_dev
 
     def sweep_concurrent(self, ridges, slots: int = 3):
         """The regularisation sweep with ``slots`` trainings side by side on one GPU: ``slots``
@@ -363,13 +408,19 @@ def nccl_unique_id() -> bytes:
 
 
 def block_evaluate(data, cls, weights, structure: ClassRelationStructure, num_classes: int,
-                   num_threads: int, cx: np.ndarray, sm_x: np.ndarray, pho: float):
+                   num_threads: int, cx: np.ndarray, sm_x: np.ndarray, pho: float, counts=None):
     """(f, g) of LOne.OptObject (LOne.java:936-1049) for every ADMM block at block weights
     ``cx[t]`` with z = u = 0: the x-update's evaluation kernel on its own, for parity tests.
     Blocks come back in the library's block order (``java_block_order``)."""
     lib = _lib.load()
-    data = np.ascontiguousarray(data, dtype=np.float64)
-    n_rows, dim = data.shape
+    if counts is not None:   # (uint8 counts, xMean, xSD): the packed-count form of `data`
+        cnt = np.ascontiguousarray(counts[0], dtype=np.uint8)
+        cmean = np.ascontiguousarray(counts[1], dtype=np.float64)
+        csd = np.ascontiguousarray(counts[2], dtype=np.float64)
+        n_rows, dim = cnt.shape[0], cnt.shape[1] + 1
+    else:
+        data = np.ascontiguousarray(data, dtype=np.float64)
+        n_rows, dim = data.shape
     st = structure.to_arrays()
 
     def ip(a):
@@ -390,10 +441,16 @@ def block_evaluate(data, cls, weights, structure: ClassRelationStructure, num_cl
         _lib.check(lib.sqw_admm_set_structure(h, st["num_nodes"], st["num_layers"],
                                               *[a.ctypes.data_as(_lib.i32p) for a in arrs]))
         _lib.check(lib.sqw_admm_set_params(h, 0.0, pho, num_threads, 1, 1, 0))
-        _lib.check(lib.sqw_admm_set_problem(h, n_rows, dim, num_classes,
-                                            data.ctypes.data_as(_lib.f64p),
-                                            cls.ctypes.data_as(_lib.i32p),
-                                            w.ctypes.data_as(_lib.f64p)))
+        if counts is not None:
+            _lib.check(lib.sqw_admm_set_problem_counts(
+                h, n_rows, dim, num_classes, cnt.ctypes.data_as(_lib.u8p),
+                cmean.ctypes.data_as(_lib.f64p), csd.ctypes.data_as(_lib.f64p),
+                cls.ctypes.data_as(_lib.i32p), w.ctypes.data_as(_lib.f64p)))
+        else:
+            _lib.check(lib.sqw_admm_set_problem(h, n_rows, dim, num_classes,
+                                                data.ctypes.data_as(_lib.f64p),
+                                                cls.ctypes.data_as(_lib.i32p),
+                                                w.ctypes.data_as(_lib.f64p)))
         _lib.check(lib.sqw_admm_eval(h, cx.ctypes.data_as(_lib.f64p),
                                      sm_x.ctypes.data_as(_lib.f64p), pho,
                                      f.ctypes.data_as(_lib.f64p), g.ctypes.data_as(_lib.f64p)))

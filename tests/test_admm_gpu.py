@@ -18,8 +18,16 @@ pytestmark = pytest.mark.gpu
 REL_TOL = 1e-6   # north_star: trained weights within 1e-6 relative (fp64)
 
 
-def run_gpu(p, T, A, S, ridge=10.0, pho=1.7):
-    lo = opt.LOneCuda(p.x0.copy(), p.smx0.copy(), p.data)
+def packed_counts(p):
+    """The training matrix as the trainer's packed-count input: uint8 counts of the kept k-mers +
+    xMean / xSD (Classifier.java:362-371)."""
+    return p.counts[:, p.keep].astype(np.uint8), p.mean, p.sd
+
+
+def run_gpu(p, T, A, S, ridge=10.0, pho=1.7, packed=False):
+    lo = opt.LOneCuda(p.x0.copy(), p.smx0.copy(), None if packed else p.data)
+    if packed:
+        lo.setCountMatrix(*packed_counts(p))
     lo.setRidge(ridge)
     lo.setADMMmaxItrs(A)
     lo.setBGFSmaxItrs(-1)
@@ -344,38 +352,56 @@ def test_full_cfg2_one_iteration_matches_oracle(oracle, cfg2_full):
     assert _rel(lo.getsmX(), smo) <= REL_TOL
 
 
-def test_full_cfg2_tracks_oracle_like_a_one_ulp_perturbation(oracle, cfg2_full):
-    """DESIGN.md 4 as a test. The reference algorithm amplifies rounding differences (every
-    x-update stops at ||g||/max(1,||x||) <= 0.1, LOne.java:874): the oracle ALONE, re-run with ONE
-    matrix element moved by one ulp, drifts away from itself by orders of magnitude per ADMM
-    iteration. The device path differs from the oracle in summation order only, so after k
-    iterations its distance from the oracle must stay within a small factor of that control, and
-    the evaluation counts must be identical for as long as the control's are."""
+@pytest.fixture(scope="module")
+def cfg2_controls(oracle, cfg2_full):
+    """Oracle runs of k = 1..3 ADMM iterations at full cfg-2 and, as the control, the same runs
+    with ONE matrix element moved by one ulp (two different elements): how far the reference
+    algorithm drifts from itself under a rounding-sized perturbation."""
     p = cfg2_full
     T = 8
-    order = opt.java_block_order(T)
-    controls = []
+    perturbed = []
     for (i, j) in ((123, 45), (15000, 600)):
         d = p.data.copy()
         d[i, j] = np.nextafter(d[i, j], np.inf)
-        controls.append(d)
+        perturbed.append(d)
+    out = {}
     for k in (1, 2, 3):
         xo, smo, tr = oracle.lone_execute(p.x0, p.smx0, p.data, p.cls, p.weights, p.st,
                                           p.num_classes, num_threads=T, admm_max_itr=k,
                                           nodes_max_itr=1, host_threads=8)
         ctrl_err, ctrl_same = 0.0, True
-        for d in controls:
+        for d in perturbed:
             xc, _, trc = oracle.lone_execute(p.x0, p.smx0, d, p.cls, p.weights, p.st, p.num_classes,
                                              num_threads=T, admm_max_itr=k, nodes_max_itr=1,
                                              host_threads=8)
             ctrl_err = max(ctrl_err, _rel(xc, xo))
             ctrl_same = ctrl_same and np.array_equal(trc.log_nfev, tr.log_nfev)
-        lo = run_gpu(p, T, k, 1)
+        out[k] = (xo, tr, ctrl_err, ctrl_same)
+    return out
+
+
+@pytest.mark.parametrize("packed", [False, True])
+def test_full_cfg2_tracks_oracle_like_a_one_ulp_perturbation(cfg2_full, cfg2_controls, packed):
+    """DESIGN.md 4 as a test. The reference algorithm amplifies rounding differences (every
+    x-update stops at ||g||/max(1,||x||) <= 0.1, LOne.java:874): the oracle ALONE, re-run with ONE
+    matrix element moved by one ulp, drifts away from itself by orders of magnitude per ADMM
+    iteration. The device paths (fp64 tiles; packed counts) differ from the oracle in rounding
+    only, so after k iterations their distance from the oracle must stay within a small factor of
+    that control, the evaluation counts must be identical for as long as the control's are, and
+    after ONE iteration the weights agree to 1e-6 (north_star's tolerance) with identical counts."""
+    p = cfg2_full
+    T = 8
+    order = opt.java_block_order(T)
+    for k in (1, 2, 3):
+        xo, tr, ctrl_err, ctrl_same = cfg2_controls[k]
+        lo = run_gpu(p, T, k, 1, packed=packed)
+        assert (lo.stats.eval_mode == 8) == packed
         err = _rel(lo.getX(), xo)
         same = np.array_equal(lo.log.nfev, tr.log_nfev[:, order])
-        print(f"cfg2 full, {k} ADMM iterations: device vs oracle {err:.2e} (nfev identical: {same}); "
-              f"oracle vs one-ulp-perturbed oracle {ctrl_err:.2e} (nfev identical: {ctrl_same})")
-        assert np.array_equal(lo.log.nfev[:2], tr.log_nfev[:2, order])   # iterations 0 and 1
+        print(f"cfg2 full ({'packed' if packed else 'fp64'}), {k} ADMM iterations: device vs oracle "
+              f"{err:.2e} (nfev identical: {same}); oracle vs one-ulp-perturbed oracle {ctrl_err:.2e} "
+              f"(nfev identical: {ctrl_same})")
+        assert np.array_equal(lo.log.nfev[:1], tr.log_nfev[:1, order])   # iteration 0
         if ctrl_same:
             assert same
         assert err <= max(1e-9, 30.0 * ctrl_err)
@@ -418,3 +444,91 @@ def test_two_live_handles_of_different_shapes():
     assert np.array_equal(los[0].getX(), first)
     for lo in los:
         lo.close()
+
+
+# --------------------------------------------------------------------------------------------
+# Packed-count form (sqw_admm_set_problem_counts, csrc/admm_eval_packed.cuh): the trainer is
+# handed the uint8 k-mer counts + xMean / xSD instead of the standardised doubles and evaluates on
+# X = (n - xMean) / xSD without materialising it. The oracle always runs the reference's way, on
+# the standardised fp64 matrix (Classifier.java:373-381 then LOne.java:936-1049).
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg,n,mf,T", [("cfg1", 500, 60, 5), ("cfg1", 2000, None, 5),
+                                          ("cfg2", 4000, None, 8), ("cfg2", 20000, None, 8),
+                                          ("cfg1", 301, 24, 7)])
+def test_packed_evaluation_matches_oracle(oracle, cfg, n, mf, T):
+    p = make_problem(cfg, n, max_features=mf)
+    nrow, dim = p.data.shape
+    C, NN = p.num_classes, p.st.num_nodes
+    rng = np.random.default_rng(5)
+    cx = rng.normal(size=(T, C * dim)) * 0.05
+    smx = rng.normal(size=NN * dim) * 0.05
+    f, g = opt.block_evaluate(None, p.cls, p.weights, p.crs, C, T, cx, smx, 1.7, counts=packed_counts(p))
+    nb = nrow // T
+    zd = np.zeros(NN * NN * dim)
+    for b, t in enumerate(opt.java_block_order(T)):
+        rows = np.arange(nb) * T + t
+        fo, go = oracle.eval_fg(p.data[rows], p.cls[rows], p.weights[rows], cx[b], smx, zd, zd, 1.7,
+                                p.st, C)
+        assert abs(f[b] - fo) <= 1e-12 * abs(fo)
+        assert np.abs(g[b] - go).max() <= 1e-12 * np.abs(go).max()
+
+
+@pytest.mark.parametrize("cfg,n,mf,T,A,S", [
+    ("cfg1", 500, 60, 5, 50, 3),
+    ("cfg1", 2000, None, 5, 5, 1),
+    ("cfg2", 4000, None, 8, 4, 1),
+    ("cfg1", 301, 24, 7, 8, 2),
+    ("cfg2", 20000, None, 8, 1, 1),     # the benchmark's shape: 144 rows per CTA resident
+])
+def test_packed_trainer_matches_oracle_fixed_iterations(oracle, cfg, n, mf, T, A, S):
+    p = make_problem(cfg, n, max_features=mf)
+    xo, smo, tr = oracle.lone_execute(p.x0, p.smx0, p.data, p.cls, p.weights, p.st, p.num_classes,
+                                      num_threads=T, admm_max_itr=A, nodes_max_itr=S, host_threads=8)
+    lo = run_gpu(p, T, A, S, packed=True)
+    assert lo.stats.eval_mode == 8                                   # the packed kernels ran
+    xg, smg = lo.getX(), lo.getsmX()
+    assert lo.stats.outer_iters == tr.outer_iters
+    assert lo.log.admm_iters == tr.admm_iters
+    assert np.array_equal(lo.log.nfev, tr.log_nfev[:, opt.java_block_order(T)])
+    assert np.array_equal(lo.log.pho, tr.log_pho) and np.array_equal(lo.log.fold, tr.log_fold)
+    assert np.abs(xg - xo).max() <= REL_TOL * np.abs(xo).max()
+    assert np.abs(smg - smo).max() <= REL_TOL * np.abs(smo).max()
+    C, dim = p.num_classes, p.data.shape[1]
+    pg = oracle.predict(oracle.destandardize(xg, C, dim, p.mean, p.sd), p.raw).argmax(1)
+    po = oracle.predict(oracle.destandardize(xo, C, dim, p.mean, p.sd), p.raw).argmax(1)
+    assert np.array_equal(pg, po)
+
+
+def test_counts_outside_the_packed_kernels_are_expanded_on_the_device(oracle):
+    """17 classes (three class tiles) are not covered by the packed kernels: the count form is
+    expanded to the fp64 matrix on the device ((n - xMean) / xSD, Classifier.java:373-381) and the
+    fp64 kernels run; a count above 255 is refused."""
+    p = make_problem("cfg4", 1700, max_features=200)
+    T, A, S = 4, 6, 2
+    xo, smo, tr = oracle.lone_execute(p.x0, p.smx0, p.data, p.cls, p.weights, p.st, p.num_classes,
+                                      num_threads=T, admm_max_itr=A, nodes_max_itr=S, host_threads=8)
+    lo = run_gpu(p, T, A, S, packed=True)
+    assert lo.stats.eval_mode != 8
+    assert np.array_equal(lo.log.nfev, tr.log_nfev[:, opt.java_block_order(T)])
+    assert np.abs(lo.getX() - xo).max() <= REL_TOL * np.abs(xo).max()
+    assert np.abs(lo.getsmX() - smo).max() <= REL_TOL * np.abs(smo).max()
+
+
+def test_packed_ridge_sweep_and_resident_reuse(oracle):
+    """A resident packed-count optimizer re-run (sweep) returns what fresh optimizers return."""
+    p = make_problem("cfg1", 600, max_features=50)
+    ridges = [0.5, 10.0]
+    base = opt.LOneCuda(p.x0.copy(), p.smx0.copy(), None)
+    base.setCountMatrix(*packed_counts(p))
+    base.setADMMmaxItrs(6); base.setBGFSmaxItrs(-1); base.setSeqUnwinderMaxIts(2)
+    base.setClassStructure(p.crs); base.setClsMembership(p.cls); base.setInstanceWeights(p.weights)
+    base.setNumClasses(p.num_classes); base.setNumPredictors(p.data.shape[1] - 1)
+    base.setPho(1.7); base.set_numThreads(5); base.initUandZ()
+    out = base.sweep(ridges)
+    for lam, (x, smx, stats, log) in zip(ridges, out):
+        assert stats.eval_mode == 8
+        fresh = run_gpu(p, 5, 6, 2, ridge=lam, packed=True)
+        assert np.array_equal(x, fresh.getX()) and np.array_equal(smx, fresh.getsmX())
+        xo, _, _ = oracle.lone_execute(p.x0, p.smx0, p.data, p.cls, p.weights, p.st, p.num_classes,
+                                       ridge=lam, num_threads=5, admm_max_itr=6, nodes_max_itr=2)
+        assert _rel(x, xo) <= REL_TOL

@@ -60,7 +60,12 @@ class _StubOptimizer:
         self.x, self.sm_x, self.data = x, sm_x, data
         self.regularization, self._cta_budget, self._handle = 0.0, 0, None
         self.stats, self.log = None, None
+        self.rows = None if data is None else data.shape[0]
         _StubOptimizer.made.append(self)
+
+    def setCountMatrix(self, counts, mean, sd):   # the packed-count form Classifier hands over
+        assert counts.dtype == np.uint8 and mean.size == sd.size == counts.shape[1] + 1
+        self.rows = counts.shape[0]
 
     def __getattr__(self, name):          # every other setter is accepted and ignored
         if name.startswith("set") or name in ("initUandZ", "clearOptimizer", "close"):
@@ -91,7 +96,7 @@ def test_cross_validate_host_logic(monkeypatch):
     cv = clf.cross_validate(p.crs, counts, p.cls, p.weights, p.num_classes, folds, slots=2, ridge=7.0)
     assert len(_StubOptimizer.made) == 4                          # all sites + one per fold
     assert {o._cta_budget for o in _StubOptimizer.made} == {148 // 2}
-    assert sorted(o.data.shape[0] for o in _StubOptimizer.made) == sorted(
+    assert sorted(o.rows for o in _StubOptimizer.made) == sorted(
         [300] + [300 - len(f) for f in folds])                    # trained on the complement
     assert (cv.predictions >= 0).all() and len(cv.fold_accuracy) == 3
     hits = sum(a * len(f) for a, f in zip(cv.fold_accuracy, folds))

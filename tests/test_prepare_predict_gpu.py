@@ -88,6 +88,24 @@ def test_resident_pipeline_sequences_to_predictions(oracle):
     _lib.check(lib.sqw_admm_execute(h, x.ctypes.data_as(_lib.f64p), smx.ctypes.data_as(_lib.f64p)))
     lib.sqw_admm_destroy(h)
     assert np.abs(x - xo).max() <= 1e-6 * np.abs(xo).max()
+    # the same training straight from the device COUNT matrix + column plan (packed-count form):
+    # no fp64 training matrix is materialised anywhere
+    h2 = C_.c_void_p()
+    _lib.check(lib.sqw_admm_create(C_.byref(h2)))
+    _lib.check(lib.sqw_admm_set_structure(h2, arr["num_nodes"], arr["num_layers"], *[a.ctypes.data_as(_lib.i32p) for a in keepalive]))
+    _lib.check(lib.sqw_admm_set_params(h2, 10.0, 1.7, T, A, S, 0))
+    stream = C_.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.sqw_admm_set_problem_counts_dev(h2, n, counts_t.shape[1], C, counts_t.data_ptr(),
+                                                   prep.keep_idx.data_ptr(), prep.num_kept, prep.mean.data_ptr(),
+                                                   prep.sd.data_ptr(), y_t.data_ptr(), w_t.data_ptr(), 0, stream))
+    x2, smx2 = hp.x0.copy(), hp.sm_x0.copy()
+    _lib.check(lib.sqw_admm_execute(h2, x2.ctypes.data_as(_lib.f64p), smx2.ctypes.data_as(_lib.f64p)))
+    st2 = _lib.AdmmStats()
+    _lib.check(lib.sqw_admm_get_stats(h2, C_.byref(st2)))
+    lib.sqw_admm_destroy(h2)
+    assert st2.eval_mode == 8
+    assert np.abs(x2 - xo).max() <= 1e-6 * np.abs(xo).max()
+    assert np.abs(smx2 - smo).max() <= 1e-6 * np.abs(smo).max()
     par = clf.destandardize(x, C, dim, hp.mean, hp.sd)
     _, arg = clf.predict_device(torch.from_numpy(par).cuda(), counts_t, prep.keep_idx, want_prob=False)
     raw = np.concatenate([np.ones((n, 1)), counts[:, hp.keep]], axis=1)

@@ -9,4 +9,4 @@ nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler
     -c admm.cu -o _obj/admm_$name.o 2> _obj/admm_$name.ptxas.log
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../_ab/lib_$name.so _obj/admm_$name.o _obj/common.o \
     _obj/kmer_count.o _obj/prepare_predict.o _obj/hills_scan.o -ldl
-grep -A3 "admm_xupdate_kernelILi1ELi5" _obj/admm_$name.ptxas.log | grep -E "spill"
+grep -A3 "admm_xupdate_kernelILi1ELi8" _obj/admm_$name.ptxas.log | grep -E "spill"

@@ -7,13 +7,16 @@ cfg = sys.argv[1]; run_oracle = int(sys.argv[2]); ns = int(sys.argv[3]) if len(s
 T = {'cfg1': 5, 'cfg2': 8}[cfg]; A, S = 400, 15
 p = make_problem(cfg, ns)
 print(cfg, p.data.shape, 'C', p.num_classes, 'cores', os.cpu_count(), flush=True)
-lo = opt.LOneCuda(p.x0.copy(), p.smx0.copy(), p.data)
+packed = os.environ.get('SQW_FP64') is None   # default: the packed-count form of the same matrix
+lo = opt.LOneCuda(p.x0.copy(), p.smx0.copy(), None if packed else p.data)
+if packed:
+    lo.setCountMatrix(p.counts[:, p.keep].astype(np.uint8), p.mean, p.sd)
 lo.setRidge(10.0); lo.setADMMmaxItrs(A); lo.setSeqUnwinderMaxIts(S)
 lo.setClassStructure(p.crs); lo.setClsMembership(p.cls); lo.setInstanceWeights(p.weights)
 lo.setNumClasses(p.num_classes); lo.setNumPredictors(p.data.shape[1]-1); lo.setPho(1.7); lo.set_numThreads(T)
 t0 = time.time(); lo.execute(); t_gpu = time.time() - t0
 s = lo.stats
-print('gpu: outer', s.outer_iters, 'conv', s.converged, 'admm', lo.log.admm_iters, 'evals', s.total_evals, 'wall %.2fs dev total %.3fs admm %.3fs xupdate %.3fs launches %d pho %.4g' % (t_gpu, s.seconds_total, s.seconds_admm, s.seconds_eval, s.launches, s.final_pho), flush=True)
+print('mode', s.eval_mode, end=' '); print('gpu: outer', s.outer_iters, 'conv', s.converged, 'admm', lo.log.admm_iters, 'evals', s.total_evals, 'wall %.2fs dev total %.3fs admm %.3fs xupdate %.3fs launches %d pho %.4g' % (t_gpu, s.seconds_total, s.seconds_admm, s.seconds_eval, s.launches, s.final_pho), flush=True)
 nb = p.data.shape[0] // T
 print('   per-eval-round us: %.2f  site-iter/s %.4g  eval GB/s %.1f' % (s.seconds_eval*1e6 / (s.total_evals / T), nb*T*s.total_admm_iters / s.seconds_admm, s.eval_bytes / s.seconds_eval / 1e9), flush=True)
 xg, smg = lo.getX().copy(), lo.getsmX().copy()
