@@ -224,6 +224,17 @@ int sqw_admm_get_log(const sqw_admm *h, int32_t cap, int32_t *rows_out, int32_t 
 int sqw_prepare_plan_dev(const int32_t *d_counts, int64_t n, int64_t numK, const double *d_w,
                          double total_weight, int32_t *d_keep_idx, int32_t *num_kept_out,
                          double *d_mean, double *d_sd, void *stream);
+/* The same in two steps, for rows sharded over ranks (path 1 shards by rows): every
+ * rank computes the per-column statistics of ITS rows (min, max, sum w x, sum w x^2; numK each),
+ * the caller combines the four arrays across ranks (min / max / sum / sum, e.g. an all-reduce) and
+ * every rank finishes with the global total_weight and row count. sqw_prepare_plan_dev is
+ * stats + finish on one rank. */
+int sqw_prepare_stats_dev(const int32_t *d_counts, int64_t n, int64_t numK, const double *d_w,
+                          int32_t *d_min, int32_t *d_max, double *d_swx, double *d_swxx, void *stream);
+int sqw_prepare_finish_dev(const int32_t *d_min, const int32_t *d_max, const double *d_swx,
+                           const double *d_swxx, int64_t numK, double total_weight, int64_t n_total,
+                           int32_t *d_keep_idx, int32_t *num_kept_out, double *d_mean, double *d_sd,
+                           void *stream);
 
 /* f-1b. The standardised training matrix the trainer takes: d_X is n x (num_kept+1) fp64
  * row-major, column 0 == 1 (Classifier.java:344,374-381). Replaces the tmpCounts.mat -> CSVLoader

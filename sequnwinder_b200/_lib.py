@@ -66,6 +66,11 @@ SYMBOLS = {
                                    f64p, i32p, i32p]),
     "sqw_prepare_plan_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_double,
                                        C.c_void_p, i32p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sqw_prepare_stats_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sqw_prepare_finish_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                         C.c_double, C.c_int64, C.c_void_p, i32p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p]),
     "sqw_prepare_apply_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int32,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sqw_predict_dev": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int64,

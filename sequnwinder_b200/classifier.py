@@ -314,6 +314,63 @@ def prepare_device(counts, weights) -> DevicePrepared:
     return DevicePrepared(X, keep, mean, sd)
 
 
+def plan_device(counts, weights, total_weight=None, n_total=None, group=None, extra=None) -> DevicePrepared:
+    """The column plan only (keep_idx, xMean, xSD; ``X`` is None): what the packed-count trainer
+    entry point needs (``LOneCuda.setCountMatrixDevice``). With ``group`` (a torch.distributed
+    process group, or True for the default one) the rows are sharded over the ranks: every rank
+    passes ITS rows, the per-column statistics are combined with all-reduces (min / max / sum) and
+    every rank gets the plan of the whole matrix; ``total_weight`` / ``n_total`` are then the
+    global sums (computed with an all-reduce when omitted). ``extra`` = (counts2, weights2): further
+    rows of this rank that take part in the statistics (e.g. the rows the ADMM blocking drops)."""
+    import ctypes as C
+    import torch
+    from . import _lib
+
+    lib = _lib.load()
+    n, numK = counts.shape
+    dev = counts.device
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    mn = torch.empty(numK, dtype=torch.int32, device=dev)
+    mx = torch.empty(numK, dtype=torch.int32, device=dev)
+    swx = torch.empty(numK, dtype=torch.float64, device=dev)
+    swxx = torch.empty(numK, dtype=torch.float64, device=dev)
+    _lib.check(lib.sqw_prepare_stats_dev(counts.data_ptr(), n, numK, weights.data_ptr(), mn.data_ptr(),
+                                         mx.data_ptr(), swx.data_ptr(), swxx.data_ptr(), stream))
+    tot = weights.sum().reshape(1)
+    cnt = torch.tensor([float(n)], dtype=torch.float64, device=dev)
+    if extra is not None and extra[0].shape[0] > 0:
+        c2, w2 = extra
+        mn2, mx2, swx2, swxx2 = (torch.empty_like(t) for t in (mn, mx, swx, swxx))
+        _lib.check(lib.sqw_prepare_stats_dev(c2.data_ptr(), c2.shape[0], numK, w2.data_ptr(), mn2.data_ptr(),
+                                             mx2.data_ptr(), swx2.data_ptr(), swxx2.data_ptr(), stream))
+        mn, mx = torch.minimum(mn, mn2), torch.maximum(mx, mx2)
+        swx, swxx = swx + swx2, swxx + swxx2
+        tot = tot + w2.sum().reshape(1)
+        cnt = cnt + float(c2.shape[0])
+    if group is not None:
+        import torch.distributed as dist
+        g = None if group is True else group
+        dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=g)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=g)
+        dist.all_reduce(swx, op=dist.ReduceOp.SUM, group=g)
+        dist.all_reduce(swxx, op=dist.ReduceOp.SUM, group=g)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=g)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=g)
+    tw = float(tot.item()) if total_weight is None else float(total_weight)
+    nt = int(cnt.item()) if n_total is None else int(n_total)
+    keep = torch.empty(numK, dtype=torch.int32, device=dev)
+    mean = torch.empty(numK, dtype=torch.float64, device=dev)
+    sd = torch.empty(numK, dtype=torch.float64, device=dev)
+    nk = C.c_int32(0)
+    rc = lib.sqw_prepare_finish_dev(mn.data_ptr(), mx.data_ptr(), swx.data_ptr(), swxx.data_ptr(), numK,
+                                    tw, nt, keep.data_ptr(), C.byref(nk), mean.data_ptr(), sd.data_ptr(),
+                                    stream)
+    if rc == _lib.SQW_ERR_INVALID_ARG and b"Sum of weights" in lib.sqw_last_error():
+        raise ValueError("Sum of weights of instances less than 1, please reweight!")
+    _lib.check(rc)
+    return DevicePrepared(None, keep[:nk.value].contiguous(), mean, sd)
+
+
 def predict_device(par, counts, keep_idx, want_prob: bool = True):
     """par: cuda fp64 [dim, C] (m_Par); counts: cuda int32 [n, numK]; keep_idx: cuda int32 [dim-1].
     Returns (prob [n, C] or None, argmax [n] int32). Classifier.java:244-287 on the GPU."""

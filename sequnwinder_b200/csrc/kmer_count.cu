@@ -25,6 +25,8 @@
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <cstring>
+#include <thread>
 #include <vector>
 
 namespace sqw {
@@ -464,6 +466,259 @@ static int launch_kmer(const uint8_t *d_bases, const int64_t *d_offsets, int64_t
     return SQW_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Host-buffer path (what the Java side calls through JNI: MakeArff.java:347-368 with the sequences
+// and the int[n][numK] matrix in host memory).
+//
+// The dense matrix is 4 numK bytes per row on the host side of PCIe (5 120 B at k = 4..5) but only
+// the canonical columns (k-mer <= reverse complement: 648 of 1 280) can be non-zero, and a count
+// never exceeds the number of windows of a row. So when max_len - kmin + 1 <= 255 the device
+// compacts the rows to one byte per canonical column, the copy goes into a pinned staging buffer
+// (648 B per row instead of 5 120 B through pageable memory), and host threads expand it into the
+// caller's dense int32 rows (zero-fill + scatter) while the next chunk is in flight. Bit-exact
+// with the dense path by construction. Buffers, streams and the pinned staging ring are
+// per-thread and persist between calls.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+kmer_compact_kernel(const int32_t *dense, int64_t rows, int64_t numK, const int32_t *canon, int ncanon,
+                    uint8_t *out)
+{
+    for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+        const int32_t *in = dense + r * numK;
+        uint8_t *o = out + r * ncanon;
+        for (int j = threadIdx.x; j < ncanon; j += blockDim.x)
+            o[j] = (uint8_t)in[canon[j]];
+    }
+}
+
+struct KmerHostCtx {
+    int device = -1;
+    cudaStream_t st[2] = {nullptr, nullptr};
+    uint8_t *d_bases[2] = {nullptr, nullptr};
+    int64_t *d_off[2] = {nullptr, nullptr};
+    int32_t *d_counts[2] = {nullptr, nullptr};
+    uint8_t *d_hasn[2] = {nullptr, nullptr};
+    uint8_t *d_compact[2] = {nullptr, nullptr};
+    uint8_t *h_stage[2] = {nullptr, nullptr};   // pinned: compact rows | has_n
+    int64_t *h_off[2] = {nullptr, nullptr};     // pinned: chunk-relative offsets
+    size_t cap_bases = 0, cap_rows = 0, cap_dense = 0, cap_stage = 0;
+    int32_t *d_status = nullptr;
+    int32_t *d_canon = nullptr;
+    std::vector<int32_t> canon;
+    int ck_min = -1, ck_max = -1;
+
+    void release()
+    {
+        if (device < 0)
+            return;
+        for (int i = 0; i < 2; ++i) {
+            if (d_bases[i]) cudaFree(d_bases[i]);
+            if (d_off[i]) cudaFree(d_off[i]);
+            if (d_counts[i]) cudaFree(d_counts[i]);
+            if (d_hasn[i]) cudaFree(d_hasn[i]);
+            if (d_compact[i]) cudaFree(d_compact[i]);
+            if (h_stage[i]) cudaFreeHost(h_stage[i]);
+            if (h_off[i]) cudaFreeHost(h_off[i]);
+            if (st[i]) cudaStreamDestroy(st[i]);
+            d_bases[i] = nullptr; d_off[i] = nullptr; d_counts[i] = nullptr; d_hasn[i] = nullptr;
+            d_compact[i] = nullptr; h_stage[i] = nullptr; h_off[i] = nullptr; st[i] = nullptr;
+        }
+        if (d_status) cudaFree(d_status);
+        if (d_canon) cudaFree(d_canon);
+        d_status = nullptr; d_canon = nullptr;
+        cap_bases = cap_rows = cap_dense = cap_stage = 0;
+        ck_min = ck_max = -1;
+        device = -1;
+        cudaGetLastError();
+    }
+    ~KmerHostCtx() { release(); }  // (at process exit the calls fail harmlessly)
+};
+
+static void canonical_columns(int kmin, int kmax, std::vector<int32_t> &out)
+{
+    out.clear();
+    int64_t base = 0;
+    for (int k = kmin; k <= kmax; ++k) {
+        const int64_t nk = (int64_t)1 << (2 * k);
+        for (int64_t v = 0; v < nk; ++v) {
+            int64_t rcv = 0, t = v;
+            for (int i = 0; i < k; ++i) {  // reverse complement: reverse the base order, 3 - base
+                rcv = (rcv << 2) | (3 - (t & 3));
+                t >>= 2;
+            }
+            if (v <= rcv)
+                out.push_back((int32_t)(base + v));
+        }
+        base += nk;
+    }
+}
+
+// zero-fill + scatter of `rows` compact rows into the caller's dense int32 rows, on host threads
+static void expand_rows(const uint8_t *stage, int64_t rows, const std::vector<int32_t> &canon,
+                        int64_t numK, int32_t *out)
+{
+    const int ncanon = (int)canon.size();
+    auto work = [&](int64_t a, int64_t b) {
+        for (int64_t r = a; r < b; ++r) {
+            int32_t *o = out + r * numK;
+            memset(o, 0, (size_t)numK * sizeof(int32_t));
+            const uint8_t *in = stage + r * ncanon;
+            for (int j = 0; j < ncanon; ++j)
+                o[canon[j]] = in[j];
+        }
+    };
+    const int64_t bytes = rows * numK * 4;
+    int nt = (int)std::min<int64_t>(std::max(1u, std::min(16u, std::thread::hardware_concurrency())),
+                                    std::max<int64_t>(1, bytes >> 21));  // >= 2 MB of output per thread
+    if (nt <= 1) {
+        work(0, rows);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t)
+        th.emplace_back(work, rows * t / nt, rows * (t + 1) / nt);
+    for (auto &x : th)
+        x.join();
+}
+
+static int host_kmer_count(const char *bases, const int64_t *offsets, int64_t n, int64_t max_len,
+                           int kmin, int kmax, int64_t numK, int32_t *counts, uint8_t *has_n)
+{
+    static thread_local KmerHostCtx ctx;
+    int dev = 0;
+    SQW_CUDA_CHECK(cudaGetDevice(&dev));
+    if (ctx.device != dev) {
+        ctx.release();
+        ctx.device = dev;
+    }
+    const bool compact = (max_len - kmin + 1) <= 255;
+    if (ctx.ck_min != kmin || ctx.ck_max != kmax) {
+        canonical_columns(kmin, kmax, ctx.canon);
+        if (ctx.d_canon) cudaFree(ctx.d_canon);
+        ctx.d_canon = nullptr;
+        SQW_CUDA_CHECK(cudaMalloc(&ctx.d_canon, ctx.canon.size() * sizeof(int32_t)));
+        SQW_CUDA_CHECK(cudaMemcpy(ctx.d_canon, ctx.canon.data(), ctx.canon.size() * sizeof(int32_t),
+                                  cudaMemcpyHostToDevice));
+        ctx.ck_min = kmin;
+        ctx.ck_max = kmax;
+    }
+    const int64_t ncanon = (int64_t)ctx.canon.size();
+    // Row chunks: the dense device rows of a chunk <= 512 MiB
+    const int64_t row_bytes = numK * 4;
+    int64_t chunk_rows = std::max<int64_t>(1, ((int64_t)512 << 20) / row_bytes);
+    chunk_rows = std::min(chunk_rows, n);
+    int64_t max_chunk_bases = 1;
+    for (int64_t r0 = 0; r0 < n; r0 += chunk_rows) {
+        const int64_t r1 = std::min(n, r0 + chunk_rows);
+        max_chunk_bases = std::max(max_chunk_bases, offsets[r1] - offsets[r0]);
+    }
+    // (re)allocate: grow only
+    if (!ctx.d_status)
+        SQW_CUDA_CHECK(cudaMalloc(&ctx.d_status, sizeof(int32_t)));
+    const size_t stage_row = compact ? (size_t)ncanon + 1 : 1;   // + has_n byte per row
+    const bool grow = (size_t)max_chunk_bases > ctx.cap_bases || (size_t)chunk_rows > ctx.cap_rows ||
+                      (size_t)chunk_rows * row_bytes > ctx.cap_dense ||
+                      (size_t)chunk_rows * stage_row > ctx.cap_stage;
+    if (grow) {
+        const size_t cb = std::max(ctx.cap_bases, (size_t)max_chunk_bases);
+        const size_t cr = std::max(ctx.cap_rows, (size_t)chunk_rows);
+        const size_t cd = std::max(ctx.cap_dense, (size_t)chunk_rows * row_bytes);
+        const size_t cs = std::max(ctx.cap_stage, (size_t)chunk_rows * std::max<size_t>(stage_row, (size_t)ncanon + 1));
+        const int device = ctx.device;
+        std::vector<int32_t> canon_keep = ctx.canon;
+        ctx.release();
+        ctx.device = device;
+        ctx.canon = canon_keep;
+        SQW_CUDA_CHECK(cudaMalloc(&ctx.d_status, sizeof(int32_t)));
+        SQW_CUDA_CHECK(cudaMalloc(&ctx.d_canon, ctx.canon.size() * sizeof(int32_t)));
+        SQW_CUDA_CHECK(cudaMemcpy(ctx.d_canon, ctx.canon.data(), ctx.canon.size() * sizeof(int32_t),
+                                  cudaMemcpyHostToDevice));
+        ctx.ck_min = kmin;
+        ctx.ck_max = kmax;
+        for (int i = 0; i < 2; ++i) {
+            SQW_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx.st[i], cudaStreamNonBlocking));
+            SQW_CUDA_CHECK(cudaMalloc(&ctx.d_bases[i], cb));
+            SQW_CUDA_CHECK(cudaMalloc(&ctx.d_off[i], (cr + 1) * sizeof(int64_t)));
+            SQW_CUDA_CHECK(cudaMalloc(&ctx.d_counts[i], cd));
+            SQW_CUDA_CHECK(cudaMalloc(&ctx.d_hasn[i], cr));
+            SQW_CUDA_CHECK(cudaMalloc(&ctx.d_compact[i], cs));
+            SQW_CUDA_CHECK(cudaMallocHost((void **)&ctx.h_stage[i], cs));
+            SQW_CUDA_CHECK(cudaMallocHost((void **)&ctx.h_off[i], (cr + 1) * sizeof(int64_t)));
+        }
+        ctx.cap_bases = cb;
+        ctx.cap_rows = cr;
+        ctx.cap_dense = cd;
+        ctx.cap_stage = cs;
+    }
+    SQW_CUDA_CHECK(cudaMemsetAsync(ctx.d_status, 0, sizeof(int32_t), ctx.st[0]));
+    SQW_CUDA_CHECK(cudaStreamSynchronize(ctx.st[0]));
+
+    // chunk i is enqueued (H2D, count, compact, D2H into pinned memory) before chunk i-1 is
+    // expanded on the host, so the copies of one chunk overlap the host work of the other
+    struct Pending { int64_t r0 = 0, rows = 0; bool live = false; } pend[2];
+    auto finish = [&](int b) -> int {
+        if (!pend[b].live)
+            return SQW_OK;
+        SQW_CUDA_CHECK(cudaStreamSynchronize(ctx.st[b]));
+        const int64_t r0 = pend[b].r0, rows = pend[b].rows;
+        if (compact) {
+            memcpy(has_n + r0, ctx.h_stage[b] + (size_t)rows * ncanon, (size_t)rows);
+            expand_rows(ctx.h_stage[b], rows, ctx.canon, numK, counts + r0 * numK);
+        }
+        pend[b].live = false;
+        return SQW_OK;
+    };
+    int buf = 0;
+    for (int64_t r0 = 0; r0 < n; r0 += chunk_rows, buf ^= 1) {
+        int rc = finish(buf);  // the previous use of this buffer pair
+        if (rc != SQW_OK)
+            return rc;
+        const int64_t r1 = std::min(n, r0 + chunk_rows);
+        const int64_t rows = r1 - r0;
+        const int64_t b0 = offsets[r0], nb = offsets[r1] - offsets[r0];
+        cudaStream_t st = ctx.st[buf];
+        for (int64_t r = 0; r <= rows; ++r)
+            ctx.h_off[buf][r] = offsets[r0 + r] - b0;
+        if (nb > 0)
+            SQW_CUDA_CHECK(cudaMemcpyAsync(ctx.d_bases[buf], bases + b0, (size_t)nb, cudaMemcpyHostToDevice, st));
+        SQW_CUDA_CHECK(cudaMemcpyAsync(ctx.d_off[buf], ctx.h_off[buf], (size_t)(rows + 1) * sizeof(int64_t),
+                                       cudaMemcpyHostToDevice, st));
+        rc = launch_kmer(ctx.d_bases[buf], ctx.d_off[buf], rows, max_len, kmin, kmax, ctx.d_counts[buf],
+                         ctx.d_hasn[buf], ctx.d_status, st);
+        if (rc != SQW_OK)
+            return rc;
+        if (compact) {
+            const int grid = (int)std::min<int64_t>(rows, (int64_t)kNumSMs * 16);
+            kmer_compact_kernel<<<grid, 256, 0, st>>>(ctx.d_counts[buf], rows, numK, ctx.d_canon, (int)ncanon,
+                                                      ctx.d_compact[buf]);
+            SQW_CUDA_CHECK(cudaGetLastError());
+            SQW_CUDA_CHECK(cudaMemcpyAsync(ctx.h_stage[buf], ctx.d_compact[buf], (size_t)rows * ncanon,
+                                           cudaMemcpyDeviceToHost, st));
+            SQW_CUDA_CHECK(cudaMemcpyAsync(ctx.h_stage[buf] + (size_t)rows * ncanon, ctx.d_hasn[buf], (size_t)rows,
+                                           cudaMemcpyDeviceToHost, st));
+        } else {
+            // rows too long for byte counts: the dense rows go straight into the caller's buffer
+            SQW_CUDA_CHECK(cudaMemcpyAsync(counts + r0 * numK, ctx.d_counts[buf], (size_t)rows * row_bytes,
+                                           cudaMemcpyDeviceToHost, st));
+            SQW_CUDA_CHECK(cudaMemcpyAsync(has_n + r0, ctx.d_hasn[buf], (size_t)rows, cudaMemcpyDeviceToHost, st));
+        }
+        pend[buf].r0 = r0;
+        pend[buf].rows = rows;
+        pend[buf].live = true;
+    }
+    for (int b = 0; b < 2; ++b) {
+        int rc = finish(buf ^ b);   // oldest first
+        if (rc != SQW_OK)
+            return rc;
+    }
+    int32_t status = 0;
+    SQW_CUDA_CHECK(cudaMemcpy(&status, ctx.d_status, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (status & 1)
+        return set_error(SQW_ERR_BAD_BASE, "Nonstandard nucleotide character encountered");
+    return SQW_OK;
+}
+
 }  // namespace sqw
 
 extern "C" {
@@ -496,99 +751,14 @@ int sqw_kmer_count(const char *bases, const int64_t *offsets, int64_t n, int kmi
         return set_error(SQW_ERR_INVALID_ARG, "null buffer");
     if (n == 0)
         return SQW_OK;
-
-    // Row chunks sized so one chunk's output is <= 512 MiB; two buffers / two streams overlap
-    // the D2H copy of chunk i with the kernel of chunk i+1.
-    const int64_t row_bytes = numK * 4;
-    int64_t chunk_rows = std::max<int64_t>(1, ((int64_t)512 << 20) / row_bytes);
-    chunk_rows = std::min(chunk_rows, n);
-    const int nbuf = (chunk_rows < n) ? 2 : 1;
-
-    int64_t max_len = 0, max_chunk_bases = 0;
+    int64_t max_len = 0;
     for (int64_t r = 0; r < n; ++r) {
         const int64_t len = offsets[r + 1] - offsets[r];
         if (len < 0)
             return set_error(SQW_ERR_INVALID_ARG, "offsets must be non-decreasing");
         max_len = std::max(max_len, len);
     }
-    for (int64_t r0 = 0; r0 < n; r0 += chunk_rows) {
-        const int64_t r1 = std::min(n, r0 + chunk_rows);
-        max_chunk_bases = std::max(max_chunk_bases, offsets[r1] - offsets[r0]);
-    }
-
-    uint8_t *d_bases[2] = {nullptr, nullptr};
-    int64_t *d_off[2] = {nullptr, nullptr};
-    int32_t *d_counts[2] = {nullptr, nullptr};
-    uint8_t *d_hasn[2] = {nullptr, nullptr};
-    int32_t *d_status = nullptr;
-    cudaStream_t st[2] = {nullptr, nullptr};
-    int result = SQW_OK;
-    std::vector<int64_t> rel((size_t)chunk_rows + 1);
-
-    auto cleanup = [&]() {
-        for (int i = 0; i < 2; ++i) {
-            if (d_bases[i]) cudaFree(d_bases[i]);
-            if (d_off[i]) cudaFree(d_off[i]);
-            if (d_counts[i]) cudaFree(d_counts[i]);
-            if (d_hasn[i]) cudaFree(d_hasn[i]);
-            if (st[i]) cudaStreamDestroy(st[i]);
-        }
-        if (d_status) cudaFree(d_status);
-    };
-#define SQW_TRY(expr)                                                                         \
-    do {                                                                                      \
-        cudaError_t _e = (expr);                                                              \
-        if (_e != cudaSuccess) {                                                              \
-            result = set_error(SQW_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
-            cleanup();                                                                        \
-            return result;                                                                    \
-        }                                                                                     \
-    } while (0)
-
-    SQW_TRY(cudaMalloc(&d_status, sizeof(int32_t)));
-    SQW_TRY(cudaMemset(d_status, 0, sizeof(int32_t)));
-    for (int i = 0; i < nbuf; ++i) {
-        SQW_TRY(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
-        SQW_TRY(cudaMalloc(&d_bases[i], (size_t)std::max<int64_t>(max_chunk_bases, 1)));
-        SQW_TRY(cudaMalloc(&d_off[i], (size_t)(chunk_rows + 1) * sizeof(int64_t)));
-        SQW_TRY(cudaMalloc(&d_counts[i], (size_t)chunk_rows * row_bytes));
-        SQW_TRY(cudaMalloc(&d_hasn[i], (size_t)chunk_rows));
-    }
-
-    int buf = 0;
-    for (int64_t r0 = 0; r0 < n; r0 += chunk_rows, buf ^= (nbuf - 1)) {
-        const int64_t r1 = std::min(n, r0 + chunk_rows);
-        const int64_t rows = r1 - r0;
-        const int64_t b0 = offsets[r0], nb = offsets[r1] - offsets[r0];
-        SQW_TRY(cudaStreamSynchronize(st[buf]));  // previous use of this buffer pair is done
-        for (int64_t r = 0; r <= rows; ++r)
-            rel[(size_t)r] = offsets[r0 + r] - b0;
-        if (nb > 0)
-            SQW_TRY(cudaMemcpyAsync(d_bases[buf], bases + b0, (size_t)nb, cudaMemcpyHostToDevice,
-                                    st[buf]));
-        SQW_TRY(cudaMemcpyAsync(d_off[buf], rel.data(), (size_t)(rows + 1) * sizeof(int64_t),
-                                cudaMemcpyHostToDevice, st[buf]));
-        SQW_TRY(cudaStreamSynchronize(st[buf]));  // rel[] is reused by the next chunk
-        rc = launch_kmer(d_bases[buf], d_off[buf], rows, max_len, kmin, kmax, d_counts[buf],
-                         d_hasn[buf], d_status, st[buf]);
-        if (rc != SQW_OK) {
-            cleanup();
-            return rc;
-        }
-        SQW_TRY(cudaMemcpyAsync(counts + r0 * numK, d_counts[buf], (size_t)rows * row_bytes,
-                                cudaMemcpyDeviceToHost, st[buf]));
-        SQW_TRY(cudaMemcpyAsync(has_n + r0, d_hasn[buf], (size_t)rows, cudaMemcpyDeviceToHost,
-                                st[buf]));
-    }
-    for (int i = 0; i < nbuf; ++i)
-        SQW_TRY(cudaStreamSynchronize(st[i]));
-    int32_t status = 0;
-    SQW_TRY(cudaMemcpy(&status, d_status, sizeof(int32_t), cudaMemcpyDeviceToHost));
-#undef SQW_TRY
-    cleanup();
-    if (status & 1)
-        return set_error(SQW_ERR_BAD_BASE, "Nonstandard nucleotide character encountered");
-    return SQW_OK;
+    return host_kmer_count(bases, offsets, n, max_len, kmin, kmax, numK, counts, has_n);
 }
 
 }  // extern "C"

@@ -44,10 +44,10 @@ column_stats_kernel(const int32_t *counts, const double *w, int64_t n, int64_t n
     swxx[(int64_t)chunk * numK + col] = b;
 }
 
-// ---- f-1, step 2: combine chunks in fixed order -> keep flag, mean, sd per column -------------
+// ---- f-1, step 2: combine the row chunks in fixed order ----------------------------------------
 __global__ void __launch_bounds__(256)
-column_finish_kernel(const int32_t *cmin, const int32_t *cmax, const double *swx, const double *swxx,
-                     int64_t numK, double tot_w, int32_t *keep_flag, double *mean, double *sd)
+column_combine_kernel(const int32_t *cmin, const int32_t *cmax, const double *swx, const double *swxx,
+                      int64_t numK, int32_t *omin, int32_t *omax, double *oswx, double *oswxx)
 {
     const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= numK)
@@ -60,10 +60,24 @@ column_finish_kernel(const int32_t *cmin, const int32_t *cmax, const double *swx
         a += swx[(int64_t)c * numK + col];
         b += swxx[(int64_t)c * numK + col];
     }
-    keep_flag[col] = (mn != mx) ? 1 : 0;  // weka RemoveUseless on a numeric attribute
-    const double m = a / tot_w;           // Classifier.java:366
+    omin[col] = mn;
+    omax[col] = mx;
+    oswx[col] = a;
+    oswxx[col] = b;
+}
+
+// ---- f-1, step 2b: keep flag, mean, sd per column from the combined statistics ----------------
+__global__ void __launch_bounds__(256)
+column_finish_kernel(const int32_t *cmin, const int32_t *cmax, const double *swx, const double *swxx,
+                     int64_t numK, double tot_w, int32_t *keep_flag, double *mean, double *sd)
+{
+    const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= numK)
+        return;
+    keep_flag[col] = (cmin[col] != cmax[col]) ? 1 : 0;  // weka RemoveUseless on a numeric attribute
+    const double m = swx[col] / tot_w;                    // Classifier.java:366
     mean[col] = m;
-    sd[col] = (tot_w > 1) ? sqrt(fabs(b - tot_w * m * m) / (tot_w - 1)) : 0.0;  // :367-371
+    sd[col] = (tot_w > 1) ? sqrt(fabs(swxx[col] - tot_w * m * m) / (tot_w - 1)) : 0.0;  // :367-371
 }
 
 // ---- f-1, step 3: standardised matrix [n][F+1], column 0 = 1 (Classifier.java:344,374-381) ----
@@ -141,6 +155,76 @@ predict_kernel(const double *par, int32_t dim, int32_t C, const int32_t *counts,
 
 extern "C" {
 
+// Per column over the caller's rows: min, max, sum w x, sum w x^2 (the row chunks combined in
+// fixed order). With the rows sharded over ranks every rank calls this on its own rows and the
+// caller combines the four arrays across ranks (min / max / sum) before sqw_prepare_finish_dev.
+int sqw_prepare_stats_dev(const int32_t *d_counts, int64_t n, int64_t numK, const double *d_w,
+                          int32_t *d_min, int32_t *d_max, double *d_swx, double *d_swxx, void *stream_)
+{
+    using namespace sqw;
+    int rc = require_device();
+    if (rc != SQW_OK)
+        return rc;
+    if (!d_counts || !d_w || !d_min || !d_max || !d_swx || !d_swxx || n < 1 || numK < 1)
+        return set_error(SQW_ERR_INVALID_ARG, "invalid argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    // one scratch allocation (stream ordered), released on every path
+    const size_t cells = (size_t)kRowChunks * numK;
+    unsigned char *scratch = nullptr;
+    SQW_CUDA_CHECK(cudaMallocAsync((void **)&scratch, cells * (2 * sizeof(int32_t) + 2 * sizeof(double)), st));
+    double *swx = reinterpret_cast<double *>(scratch), *swxx = swx + cells;
+    int32_t *cmin = reinterpret_cast<int32_t *>(swxx + cells), *cmax = cmin + cells;
+    const dim3 grid((unsigned)((numK + 255) / 256), kRowChunks);
+    column_stats_kernel<<<grid, 256, 0, st>>>(d_counts, d_w, n, numK, cmin, cmax, swx, swxx);
+    column_combine_kernel<<<(unsigned)((numK + 255) / 256), 256, 0, st>>>(cmin, cmax, swx, swxx, numK,
+                                                                          d_min, d_max, d_swx, d_swxx);
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(scratch, st);
+    if (e != cudaSuccess)
+        return set_error(SQW_ERR_CUDA, "prepare stats failed: %s", cudaGetErrorString(e));
+    return SQW_OK;
+}
+
+// keep flag (weka RemoveUseless: min != max), mean and SD per column from the combined statistics;
+// the kept column indices are written in ascending order. Synchronises the stream.
+int sqw_prepare_finish_dev(const int32_t *d_min, const int32_t *d_max, const double *d_swx,
+                           const double *d_swxx, int64_t numK, double total_weight, int64_t n_total,
+                           int32_t *d_keep_idx, int32_t *num_kept_out, double *d_mean, double *d_sd,
+                           void *stream_)
+{
+    using namespace sqw;
+    int rc = require_device();
+    if (rc != SQW_OK)
+        return rc;
+    if (!d_min || !d_max || !d_swx || !d_swxx || !d_keep_idx || !num_kept_out || !d_mean || !d_sd || numK < 1)
+        return set_error(SQW_ERR_INVALID_ARG, "invalid argument");
+    if ((total_weight <= 1) && (n_total > 1))  // Classifier.java:359-362
+        return set_error(SQW_ERR_INVALID_ARG, "Sum of weights of instances less than 1, please reweight!");
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    int32_t *flag = nullptr;
+    SQW_CUDA_CHECK(cudaMallocAsync((void **)&flag, (size_t)numK * sizeof(int32_t), st));
+    column_finish_kernel<<<(unsigned)((numK + 255) / 256), 256, 0, st>>>(d_min, d_max, d_swx, d_swxx, numK,
+                                                                         total_weight, flag, d_mean, d_sd);
+    std::vector<int32_t> hflag((size_t)numK);
+    cudaError_t e = cudaMemcpyAsync(hflag.data(), flag, (size_t)numK * sizeof(int32_t),
+                                    cudaMemcpyDeviceToHost, st);
+    cudaFreeAsync(flag, st);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess)
+        return set_error(SQW_ERR_CUDA, "prepare plan failed: %s", cudaGetErrorString(e));
+    std::vector<int32_t> keep;
+    for (int64_t c = 0; c < numK; ++c)
+        if (hflag[(size_t)c])
+            keep.push_back((int32_t)c);
+    *num_kept_out = (int32_t)keep.size();
+    if (!keep.empty())
+        SQW_CUDA_CHECK(cudaMemcpyAsync(d_keep_idx, keep.data(), keep.size() * sizeof(int32_t),
+                                       cudaMemcpyHostToDevice, st));
+    SQW_CUDA_CHECK(cudaStreamSynchronize(st));
+    return SQW_OK;
+}
+
 int sqw_prepare_plan_dev(const int32_t *d_counts, int64_t n, int64_t numK, const double *d_w,
                          double total_weight, int32_t *d_keep_idx, int32_t *num_kept_out,
                          double *d_mean, double *d_sd, void *stream_)
@@ -154,36 +238,16 @@ int sqw_prepare_plan_dev(const int32_t *d_counts, int64_t n, int64_t numK, const
     if ((total_weight <= 1) && (n > 1))  // Classifier.java:359-362
         return set_error(SQW_ERR_INVALID_ARG, "Sum of weights of instances less than 1, please reweight!");
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
-    int32_t *cmin = nullptr, *cmax = nullptr, *flag = nullptr;
-    double *swx = nullptr, *swxx = nullptr;
-    const size_t cells = (size_t)kRowChunks * numK;
-    SQW_CUDA_CHECK(cudaMalloc(&cmin, cells * sizeof(int32_t)));
-    SQW_CUDA_CHECK(cudaMalloc(&cmax, cells * sizeof(int32_t)));
-    SQW_CUDA_CHECK(cudaMalloc(&swx, cells * sizeof(double)));
-    SQW_CUDA_CHECK(cudaMalloc(&swxx, cells * sizeof(double)));
-    SQW_CUDA_CHECK(cudaMalloc(&flag, (size_t)numK * sizeof(int32_t)));
-    const dim3 grid((unsigned)((numK + 255) / 256), kRowChunks);
-    column_stats_kernel<<<grid, 256, 0, st>>>(d_counts, d_w, n, numK, cmin, cmax, swx, swxx);
-    column_finish_kernel<<<(unsigned)((numK + 255) / 256), 256, 0, st>>>(cmin, cmax, swx, swxx, numK,
-                                                                         total_weight, flag, d_mean, d_sd);
-    std::vector<int32_t> hflag((size_t)numK);
-    cudaError_t e = cudaMemcpyAsync(hflag.data(), flag, (size_t)numK * sizeof(int32_t),
-                                    cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess)
-        e = cudaStreamSynchronize(st);
-    cudaFree(cmin); cudaFree(cmax); cudaFree(swx); cudaFree(swxx); cudaFree(flag);
-    if (e != cudaSuccess)
-        return set_error(SQW_ERR_CUDA, "prepare plan failed: %s", cudaGetErrorString(e));
-    std::vector<int32_t> keep;
-    for (int64_t c = 0; c < numK; ++c)
-        if (hflag[(size_t)c])
-            keep.push_back((int32_t)c);
-    *num_kept_out = (int32_t)keep.size();
-    if (!keep.empty())
-        SQW_CUDA_CHECK(cudaMemcpyAsync(d_keep_idx, keep.data(), keep.size() * sizeof(int32_t),
-                                       cudaMemcpyHostToDevice, st));
-    SQW_CUDA_CHECK(cudaStreamSynchronize(st));
-    return SQW_OK;
+    unsigned char *scratch = nullptr;
+    SQW_CUDA_CHECK(cudaMallocAsync((void **)&scratch, (size_t)numK * (2 * sizeof(int32_t) + 2 * sizeof(double)), st));
+    double *swx = reinterpret_cast<double *>(scratch), *swxx = swx + numK;
+    int32_t *cmin = reinterpret_cast<int32_t *>(swxx + numK), *cmax = cmin + numK;
+    rc = sqw_prepare_stats_dev(d_counts, n, numK, d_w, cmin, cmax, swx, swxx, stream_);
+    if (rc == SQW_OK)
+        rc = sqw_prepare_finish_dev(cmin, cmax, swx, swxx, numK, total_weight, n, d_keep_idx, num_kept_out,
+                                    d_mean, d_sd, stream_);
+    cudaFreeAsync(scratch, st);
+    return rc;
 }
 
 int sqw_prepare_apply_dev(const int32_t *d_counts, int64_t n, int64_t numK, const int32_t *d_keep_idx,

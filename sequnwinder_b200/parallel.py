@@ -46,6 +46,17 @@ def block_rows(n_rows: int, T: int, t: int):
     return [t + T * s for s in range(nb)]
 
 
+def local_row_indices(n_rows: int, T: int, rank: int, world: int):
+    """Global indices of the rows that live on ``rank`` (the rows of its blocks), ascending: the
+    rows a rank featurises itself when path 1 is sharded by rows, and the row order the
+    ``rows_local`` form of ``sqw_admm_set_problem_counts_dev`` expects."""
+    import numpy as np
+
+    nb = n_rows // T
+    i = np.arange(nb * T, dtype=np.int64)
+    return i[(i % T) % world == rank]
+
+
 def local_ridges(ridges, rank: int, world: int):
     """Regularisation sweep (BASELINE config 5) on several GPUs: the solves are independent, so
     they are dealt out as replicas, no collective: value i runs on rank ``i % world``. Returns

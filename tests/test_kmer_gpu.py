@@ -28,7 +28,8 @@ def test_golden_fixtures():
             assert np.array_equal(got[i], want), (kmin, kmax, c["seq"][:16])
 
 
-@pytest.mark.parametrize("cfg,n", [("cfg1", None), ("cfg2", None), ("cfg3", 3000), ("cfg4", 20000)])
+@pytest.mark.parametrize("cfg,n", [("cfg1", None), ("cfg2", None), ("cfg3", 3000), ("cfg4", 20000),
+                                    ("cfg3", 7000)])   # 7000 x k4..7 rows: two chunks of the host path
 def test_configs_bit_exact(oracle, cfg, n):
     c = synth.CONFIGS[cfg]
     d = synth.generate_config(cfg, n, n_frac=0.005)
