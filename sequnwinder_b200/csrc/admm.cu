@@ -129,6 +129,12 @@ struct sqw_admm {
     Ctrl *h_ring = nullptr;  // pinned [kRing]
     cudaEvent_t ev_x0[kRing], ev_x1[kRing], ev_snap[kRing];
     cudaEvent_t ev_a, ev_b, ev_t0, ev_t1;
+    // SQW_ADMM_TAIL_PROFILE (multi-GPU): events between the kernels / all-reduces of the iteration
+    // tail, so that the time an iteration loses to the collective (incl. the wait for the slowest
+    // rank's x-update) is measured, not inferred
+    bool tail_prof = false;
+    cudaEvent_t ev_tail[kRing][5];
+    double tail_ms[6] = {0, 0, 0, 0, 0, 0};   // x-update, pack, all-reduce 1, consensus, all-reduce 2, decide
     // evaluation caps of the x-update phases (cumulative; the last phase runs every block to
     // completion); tuned at cfg-2 (mean 14.7, max 24 evaluations per x-update)
     int caps[kNumPhases] = {8, 12, 16, 20, 26, 0x7fffffff};
@@ -401,6 +407,12 @@ static int prepare(sqw_admm *h)
     SQW_CUDA_CHECK(cudaEventCreate(&h->ev_b));
     SQW_CUDA_CHECK(cudaEventCreate(&h->ev_t0));
     SQW_CUDA_CHECK(cudaEventCreate(&h->ev_t1));
+    if (h->world > 1 && getenv("SQW_ADMM_TAIL_PROFILE")) {
+        for (int i = 0; i < kRing; ++i)
+            for (int j = 0; j < 5; ++j)
+                SQW_CUDA_CHECK(cudaEventCreate(&h->ev_tail[i][j]));
+        h->tail_prof = true;
+    }
     h->prepared = true;
     return SQW_OK;
 }
@@ -452,12 +464,17 @@ static int enqueue_iteration(sqw_admm *h, int slot)
     }
     const int total = D.npad + D.upad;
     admm_pack_kernel<<<(total + 255) / 256, 256, 0, h->stream>>>(D);
+    if (h->tail_prof) cudaEventRecord(h->ev_tail[slot][0], h->stream);
     if ((rc = nccl_allreduce(h, D.sum1, (size_t)total)) != SQW_OK)
         return rc;
+    if (h->tail_prof) cudaEventRecord(h->ev_tail[slot][1], h->stream);
     admm_consensus_kernel<<<D.E, kThreads, 0, h->stream>>>(D);  // block_sum() needs kThreads
+    if (h->tail_prof) cudaEventRecord(h->ev_tail[slot][2], h->stream);
     if ((rc = nccl_allreduce(h, D.sum2, (size_t)D.E)) != SQW_OK)
         return rc;
+    if (h->tail_prof) cudaEventRecord(h->ev_tail[slot][3], h->stream);
     admm_decide_kernel<<<1, kDecideThreads, 0, h->stream>>>(D);
+    if (h->tail_prof) cudaEventRecord(h->ev_tail[slot][4], h->stream);
     SQW_CUDA_CHECK(cudaMemcpyAsync(&h->h_ring[slot], D.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost,
                                    h->stream));
     SQW_CUDA_CHECK(cudaEventRecord(h->ev_snap[slot], h->stream));
@@ -519,6 +536,10 @@ void sqw_admm_destroy(sqw_admm *h)
         cudaEventDestroy(h->ev_b);
         cudaEventDestroy(h->ev_t0);
         cudaEventDestroy(h->ev_t1);
+        if (h->tail_prof)
+            for (int i = 0; i < kRing; ++i)
+                for (int j = 0; j < 5; ++j)
+                    cudaEventDestroy(h->ev_tail[i][j]);
     }
     if (h->stream)
         cudaStreamDestroy(h->stream);
@@ -1109,6 +1130,16 @@ static int execute_impl(sqw_admm *h, double *x_inout, double *smx_inout)
             float ms = 0.f;
             SQW_CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev_x0[slot], h->ev_x1[slot]));
             ms_eval += ms;
+            if (h->tail_prof && !h->h_ring[slot].done) {
+                h->tail_ms[0] += ms;
+                cudaEvent_t prev = h->ev_x1[slot];
+                for (int j = 0; j < 5; ++j) {
+                    float t = 0.f;
+                    if (cudaEventElapsedTime(&t, prev, h->ev_tail[slot][j]) == cudaSuccess)
+                        h->tail_ms[1 + j] += t;
+                    prev = h->ev_tail[slot][j];
+                }
+            }
             last = h->h_ring[slot];
             ++seen;
             if (last.done || last.fatal)
@@ -1167,6 +1198,17 @@ static int execute_impl(sqw_admm *h, double *x_inout, double *smx_inout)
     if ((rc = download_padded(h, D.xbar, D.C, D.dim, D.dimp, x_inout)) != SQW_OK) return rc;
     if ((rc = download_padded(h, D.smx, D.NN, D.dim, D.dimp, smx_inout)) != SQW_OK) return rc;
 
+    if (h->tail_prof && h->stats.total_admm_iters > 0) {
+        const double it = (double)h->stats.total_admm_iters;
+        fprintf(stderr, "[sqw tail profile] rank %d, %d ADMM iterations, us per iteration: x-update (own blocks) "
+                        "%.1f | pack %.1f | all-reduce 1 incl. wait for the slowest rank %.1f | consensus %.1f | "
+                        "all-reduce 2 %.1f | decide %.1f\n",
+                h->rank, h->stats.total_admm_iters, 1e3 * h->tail_ms[0] / it, 1e3 * h->tail_ms[1] / it,
+                1e3 * h->tail_ms[2] / it, 1e3 * h->tail_ms[3] / it, 1e3 * h->tail_ms[4] / it,
+                1e3 * h->tail_ms[5] / it);
+        for (double &v : h->tail_ms)
+            v = 0.0;
+    }
     if (D.prof) {
         // thread 0 of CTA 0 (first CTA of the first unfinished block), per phase of the x-update
         std::vector<long long> pr((size_t)D.Gmax * kProfSlots * kNumPhases);
