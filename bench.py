@@ -627,7 +627,7 @@ def run_cfg2(args, info, world, dev, comm, dist, torch):
     # durations (max over ranks)
     achieved = acc["eval_bytes_all"] / world / acc["eval_s_max"] / 1e9 if acc["eval_s_max"] > 0 else 0.0
     traffic, traffic_src = ncu_traffic_per_xupdate()
-    if world != 1 or acc["stats_mode"] != 8:
+    if world != 1 or acc["stats_mode"] not in (8, 9):
         traffic, traffic_src = None, None   # the capture is of the single-GPU packed-count kernel
     kmer_bytes = sites * (LENGTH + 4 * kc.numK) * args.steps
     block_evals_per_s = acc["evals_all"] / acc["admm_s"]
@@ -640,7 +640,7 @@ def run_cfg2(args, info, world, dev, comm, dist, torch):
         json.dump(traj, open(os.path.join(ROOT, "gpurun_out", f"cfg2_trajectory_n{world}_{args.scaling}.json"), "w"))
     except Exception:
         pass
-    packed = acc["stats_mode"] == 8
+    packed = acc["stats_mode"] in (8, 9)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": acc["total_s"] / args.steps * 1e3, "higher_is_better": True,

@@ -169,45 +169,50 @@ typedef void (*EKernel)(AdmmDev, TileSmemLayout, double, double *);
 
 static XKernel xupdate_kernel(int nct, int mode)
 {
-    switch (nct * 8 + mode) {
-    case 8 + 4: return admm_xupdate_kernel<1, 4>;
-    case 8 + 6: return admm_xupdate_kernel<1, 6>;
-    case 8 + 5: return admm_xupdate_kernel<1, 5>;
-    case 8 + 8: return admm_xupdate_kernel<1, 8>;
-    case 8 + 1: return admm_xupdate_kernel<1, 1>;
-    case 8 + 2: return admm_xupdate_kernel<1, 2>;
-    case 16 + 4: return admm_xupdate_kernel<2, 4>;
-    case 16 + 6: return admm_xupdate_kernel<2, 6>;
-    case 16 + 1: return admm_xupdate_kernel<2, 1>;
-    case 16 + 2: return admm_xupdate_kernel<2, 2>;
-    case 24 + 4: return admm_xupdate_kernel<3, 4>;
-    case 24 + 6: return admm_xupdate_kernel<3, 6>;
-    case 24 + 1: return admm_xupdate_kernel<3, 1>;
-    case 24 + 2: return admm_xupdate_kernel<3, 2>;
+    switch (nct * 16 + mode) {
+    case 16 + 4: return admm_xupdate_kernel<1, 4>;
+    case 16 + 6: return admm_xupdate_kernel<1, 6>;
+    case 16 + 5: return admm_xupdate_kernel<1, 5>;
+    case 16 + 8: return admm_xupdate_kernel<1, 8>;
+    case 16 + 9: return admm_xupdate_kernel<1, 9>;
+    case 16 + 1: return admm_xupdate_kernel<1, 1>;
+    case 16 + 2: return admm_xupdate_kernel<1, 2>;
+    case 32 + 4: return admm_xupdate_kernel<2, 4>;
+    case 32 + 6: return admm_xupdate_kernel<2, 6>;
+    case 32 + 1: return admm_xupdate_kernel<2, 1>;
+    case 32 + 2: return admm_xupdate_kernel<2, 2>;
+    case 48 + 4: return admm_xupdate_kernel<3, 4>;
+    case 48 + 6: return admm_xupdate_kernel<3, 6>;
+    case 48 + 1: return admm_xupdate_kernel<3, 1>;
+    case 48 + 2: return admm_xupdate_kernel<3, 2>;
     }
     return nullptr;
 }
 
 static EKernel eval_kernel(int nct, int mode)
 {
-    switch (nct * 8 + mode) {
-    case 8 + 4: return admm_eval_kernel<1, 4>;
-    case 8 + 6: return admm_eval_kernel<1, 6>;
-    case 8 + 5: return admm_eval_kernel<1, 5>;
-    case 8 + 8: return admm_eval_kernel<1, 8>;
-    case 8 + 1: return admm_eval_kernel<1, 1>;
-    case 8 + 2: return admm_eval_kernel<1, 2>;
-    case 16 + 4: return admm_eval_kernel<2, 4>;
-    case 16 + 6: return admm_eval_kernel<2, 6>;
-    case 16 + 1: return admm_eval_kernel<2, 1>;
-    case 16 + 2: return admm_eval_kernel<2, 2>;
-    case 24 + 4: return admm_eval_kernel<3, 4>;
-    case 24 + 6: return admm_eval_kernel<3, 6>;
-    case 24 + 1: return admm_eval_kernel<3, 1>;
-    case 24 + 2: return admm_eval_kernel<3, 2>;
+    switch (nct * 16 + mode) {
+    case 16 + 4: return admm_eval_kernel<1, 4>;
+    case 16 + 6: return admm_eval_kernel<1, 6>;
+    case 16 + 5: return admm_eval_kernel<1, 5>;
+    case 16 + 8: return admm_eval_kernel<1, 8>;
+    case 16 + 9: return admm_eval_kernel<1, 9>;
+    case 16 + 1: return admm_eval_kernel<1, 1>;
+    case 16 + 2: return admm_eval_kernel<1, 2>;
+    case 32 + 4: return admm_eval_kernel<2, 4>;
+    case 32 + 6: return admm_eval_kernel<2, 6>;
+    case 32 + 1: return admm_eval_kernel<2, 1>;
+    case 32 + 2: return admm_eval_kernel<2, 2>;
+    case 48 + 4: return admm_eval_kernel<3, 4>;
+    case 48 + 6: return admm_eval_kernel<3, 6>;
+    case 48 + 1: return admm_eval_kernel<3, 1>;
+    case 48 + 2: return admm_eval_kernel<3, 2>;
     }
     return nullptr;
 }
+
+static int mode_threads(int mode) { return mode == 9 ? ModeCfg<9>::NT : kThreads; }
+static int mode_ctas_per_sm(int mode) { return mode == 9 ? ModeCfg<9>::MINB : 1; }
 
 static int upload_ints(sqw_admm *h, const std::vector<int> &v, const int **dst)
 {
@@ -265,6 +270,9 @@ static int prepare(sqw_admm *h)
     D.wstride = D.dimp;
     D.world = h->world;
     D.ridge = h->ridge;
+    D.n_sm = 148;
+    // MODE 9 probe: start delay of the second CTA of every SM (measured: no effect, see plan_blocks)
+    D.skew_ns = getenv("SQW_ADMM_SKEW_NS") ? atoi(getenv("SQW_ADMM_SKEW_NS")) : 0;
     const int nct = D.Cp / 8;
     if ((long long)D.Cp * D.dimp * h->dev.T_local > (1ll << 31) - 1 || (long long)D.upad > (1 << 30))
         return set_error(SQW_ERR_UNSUPPORTED, "problem too large for 32-bit coordinate indices");
@@ -272,11 +280,12 @@ static int prepare(sqw_admm *h)
     cudaDeviceProp prop;
     SQW_CUDA_CHECK(cudaGetDeviceProperties(&prop, h->device));
     int n_sm = prop.multiProcessorCount;
+    D.n_sm = prop.multiProcessorCount;
     if (h->cta_budget > 0)
         n_sm = std::min(n_sm, h->cta_budget);
     const int mode = h->eval_mode;
     const size_t w_bytes = (size_t)D.Cp * D.wstride * sizeof(double);
-    if (mode == 4 || mode == 5 || mode == 6 || mode == 8)
+    if (mode == 4 || mode == 5 || mode == 6 || mode == 8 || mode == 9)
         h->xupdate_smem = h->layout.total;
     else if (mode == 1)
         h->xupdate_smem = w_bytes;
@@ -298,16 +307,18 @@ static int prepare(sqw_admm *h)
         SQW_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_max));
     }
     int per_sm = 0;
-    SQW_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, xk, kThreads,
+    SQW_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, xk, mode_threads(mode),
                                                                  h->xupdate_smem));
-    if (per_sm < 1)
-        return set_error(SQW_ERR_UNSUPPORTED, "x-update kernel does not fit on an SM");
+    if (per_sm < mode_ctas_per_sm(mode))
+        return set_error(SQW_ERR_UNSUPPORTED, "x-update kernel does not fit on an SM (%d of %d CTAs)",
+                         per_sm, mode_ctas_per_sm(mode));
+    per_sm = mode_ctas_per_sm(mode);
     // one CTA per SM: G CTAs per ADMM block, all T_local groups co-resident
     if (D.T_local > n_sm * per_sm)
         return set_error(SQW_ERR_UNSUPPORTED, "%d local ADMM blocks exceed %d co-resident CTAs",
                          D.T_local, n_sm * per_sm);
     int G = 1;
-    group_sizes(h, prop.multiProcessorCount, D.T_local, D.nb, G, D.gcap);
+    group_sizes(h, prop.multiProcessorCount * per_sm, D.T_local, D.nb, G, D.gcap);
     // a rank that owns a single block has nothing to re-group: one launch, run to completion
     h->nphase = (D.T_local == 1) ? 1 : kNumPhases;
     D.nphase = h->nphase;
@@ -424,8 +435,8 @@ static int launch_xupdate(sqw_admm *h)
     for (int ph = 0; ph < h->nphase; ++ph) {
         int phase = ph, cap = (ph == h->nphase - 1) ? 0x7fffffff : h->caps[ph];
         void *args[] = {&D, &h->layout, &phase, &cap};
-        SQW_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)xk, dim3(D.Gmax), dim3(kThreads), args,
-                                                   h->xupdate_smem, h->stream));
+        SQW_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)xk, dim3(D.Gmax), dim3(mode_threads(h->eval_mode)),
+                                                   args, h->xupdate_smem, h->stream));
     }
     h->stats.launches += h->nphase - 1;
     return SQW_OK;
@@ -812,17 +823,50 @@ static int plan_blocks(sqw_admm *h, int64_t n_rows, int32_t dim, int32_t num_cla
     if (counts_form && nct == 1 && dim <= kPackedMaxDim && !getenv("SQW_ADMM_NO_PACKED") &&
         !getenv("SQW_ADMM_EVAL_MODE")) {
         const int dimp16 = (dim + 15) / 16 * 16;
-        int G = 1, gcap = 1;
-        group_sizes(h, prop.multiProcessorCount, D.T_local, D.nb, G, gcap);
-        const int gmin = std::min(G, gcap);
         const long long tiles = (D.nb + 7) / 8;
-        const int rows_cap8 = (int)((tiles + gmin - 1) / gmin) * 8;
-        TileSmemLayout Lp = packed_smem_layout(dimp16, rows_cap8, kSolveSliceBytes);
-        if (Lp.total <= budget) {
-            h->eval_mode = 8;
-            h->layout = Lp;
-            D.dimp = dimp16;
-            D.rsq = dimp16;
+        const char *force = getenv("SQW_ADMM_PACKED_MODE");   // test hook: 9
+        // MODE 9 (two CTAs of 192 threads per SM, so that one CTA evaluates while the other sits in
+        // its solver's exchange chain) is built and tested but OFF: measured at cfg-2 70.6 us per
+        // evaluation round against MODE 8's 52.3, with and without a start skew between the two
+        // CTAs of an SM - one DMMA warp per SM sub-partition reaches only half the DMMA issue rate
+        // (its byte conversions and DMMAs serialise), so a CTA alone on an SM evaluates no faster
+        // than two side by side, and the doubled groups lengthen the exchange chain.
+        if (D.T_local >= 2 && force && atoi(force) == 9) {
+            int G = 1, gcap = 1;
+            group_sizes(h, prop.multiProcessorCount * ModeCfg<9>::MINB, D.T_local, D.nb, G, gcap);
+            const int gmin = std::min(G, gcap);
+            const int rows_cap8 = (int)((tiles + gmin - 1) / gmin) * 8;
+            TileSmemLayout Lp = packed_smem_layout(dimp16, rows_cap8,
+                                                   (size_t)kSliceVectors * kPackedSliceCap2 * sizeof(double),
+                                                   ModeCfg<9>::DW);
+            int per_sm = 0;
+            cudaFuncAttributes fa;
+            const void *fn = (const void *)admm_xupdate_kernel<1, 9>;
+            if (cudaFuncGetAttributes(&fa, fn) == cudaSuccess &&
+                Lp.total + fa.sharedSizeBytes <= (size_t)prop.sharedMemPerBlockOptin &&
+                cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(prop.sharedMemPerBlockOptin - fa.sharedSizeBytes)) == cudaSuccess &&
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, ModeCfg<9>::NT, Lp.total) == cudaSuccess &&
+                per_sm >= ModeCfg<9>::MINB && (D.Cp * dimp16 + gmin - 1) / gmin <= kPackedSliceCap2 - 15) {
+                h->eval_mode = 9;
+                h->layout = Lp;
+                D.dimp = dimp16;
+                D.rsq = dimp16;
+            }
+            cudaGetLastError();
+        }
+        if (h->eval_mode != 9) {
+            int G = 1, gcap = 1;
+            group_sizes(h, prop.multiProcessorCount, D.T_local, D.nb, G, gcap);
+            const int gmin = std::min(G, gcap);
+            const int rows_cap8 = (int)((tiles + gmin - 1) / gmin) * 8;
+            TileSmemLayout Lp = packed_smem_layout(dimp16, rows_cap8, kSolveSliceBytes);
+            if (Lp.total <= budget) {
+                h->eval_mode = 8;
+                h->layout = Lp;
+                D.dimp = dimp16;
+                D.rsq = dimp16;
+            }
         }
     }
     return SQW_OK;
@@ -949,7 +993,7 @@ static int build_from_counts(sqw_admm *h, const SrcT *d_src, long long src_strid
     admm_packed_stats_kernel<<<(D.dimp + 255) / 256, 256, 0, st>>>(d_mean, d_sd, d_col_idx, D.dim, D.dimp,
                                                                    mean_p, invsd_p, mean_f, sd_f);
     const int grid = (int)std::min<size_t>(rows, 148 * 16);
-    if (h->eval_mode == 8) {
+    if (h->eval_mode == 8 || h->eval_mode == 9) {
         unsigned char *dXq = nullptr;
         if ((rc = h->dalloc(&dXq, rows * D.rsq + 16384, false)) != SQW_OK) return rc;
         admm_gather_counts_kernel<SrcT, true><<<grid, 256, 0, st>>>(
@@ -1344,7 +1388,7 @@ int sqw_admm_eval(sqw_admm *h, const double *cx, const double *smx, double pho, 
     SQW_CUDA_CHECK(cudaMemsetAsync(d_f, 0, sizeof(double) * D.T_local, st));
     EKernel ek = eval_kernel(D.Cp / 8, h->eval_mode);
     void *args[] = {&D, &h->layout, &pho, &d_f};
-    cudaError_t e = cudaLaunchCooperativeKernel((void *)ek, dim3(D.Gmax), dim3(kThreads),
+    cudaError_t e = cudaLaunchCooperativeKernel((void *)ek, dim3(D.Gmax), dim3(mode_threads(h->eval_mode)),
                                                 args, h->xupdate_smem, st);
     if (e == cudaSuccess)
         e = cudaStreamSynchronize(st);

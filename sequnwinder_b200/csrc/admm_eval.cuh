@@ -46,6 +46,7 @@ __device__ __forceinline__ double warp_sum(double v)
 }
 
 // Sum over the CTA (fixed order); result valid in every thread. `red` holds >= kWarps doubles.
+template <int NW = kWarps>
 __device__ __forceinline__ double block_sum(double v, double *red)
 {
     v = warp_sum(v);
@@ -55,7 +56,7 @@ __device__ __forceinline__ double block_sum(double v, double *red)
     __syncthreads();
     double s = 0.0;
 #pragma unroll
-    for (int i = 0; i < kWarps; ++i)
+    for (int i = 0; i < NW; ++i)
         s += red[i];
     return s;
 }

@@ -31,8 +31,9 @@
 
 namespace sqw {
 
-constexpr int kPackedNBG = 6;                       // 16-column groups per DMMA warp
-constexpr int kPackedMaxDim = 8 * kPackedNBG * 16;  // 768 columns incl. the intercept
+constexpr int kPackedMaxGroups = 48;                 // 16-column groups per row
+constexpr int kPackedMaxDim = kPackedMaxGroups * 16;  // 768 columns incl. the intercept
+constexpr int kPackedSliceCap2 = 160;                // slice-cache coordinates per vector, two CTAs per SM
 
 // no L2 hint: the packed matrix (13 MB at cfg-2) stays in L2 between the launches of an iteration
 __device__ __forceinline__ void bulk_g2s_plain(void *dst, const void *src, unsigned bytes,
@@ -48,7 +49,7 @@ __device__ __forceinline__ void bulk_g2s_plain(void *dst, const void *src, unsig
 // Shared-memory carve-up (TileSmemLayout re-used): head = the solver's slice cache, stage = the
 // CTA's rows (rows_cap8 x rsq bytes), plog = [8 warps][rows_cap8][8] partial logits (slot 0 is
 // re-used for the residuals), rs = 8 x 8 offset partials + 8 class sums, bar = one mbarrier.
-inline TileSmemLayout packed_smem_layout(int rsq, int rows_cap8, size_t slice_bytes)
+inline TileSmemLayout packed_smem_layout(int rsq, int rows_cap8, size_t slice_bytes, int kDmmaWarps = 8)
 {
     TileSmemLayout L{};
     L.w_off = 0;
@@ -65,25 +66,24 @@ inline TileSmemLayout packed_smem_layout(int rsq, int rows_cap8, size_t slice_by
     return L;
 }
 
-#ifndef SQW_PACKED_CVT_MAGIC
-#define SQW_PACKED_CVT_MAGIC 0
-#endif
-// exact conversion of a byte. I2F.F64 runs beside the DMMAs; the alternative (2^52 + v built with one
-// integer op, the 2^52 removed by a DADD) was measured slower at cfg-2 (55.7 vs 52.3 us per
-// evaluation round): the DADD shares the fp64 pipe with DMMA
+// Exact conversion of a byte count (I2F.F64 on the XU pipe). Measured alternatives at cfg-2, us per
+// evaluation round (profiles/README.md): I2F 52.3 | 2^52 + v built with one integer op and the 2^52
+// removed by a DADD 55.7 (the DADD shares the fp64 lanes the DMMA runs on) | a 256-entry
+// byte -> double table in shared memory (LDS.64) 58.9 | I2F with the conversions of column group
+// i+1 placed ahead of the DMMAs of group i in the source (volatile asm) 54.3 - ptxas keeps its own
+// order: one conversion register, I2F -> DMMA -> I2F -> DMMA, ~40 cycles per DMMA and warp, which
+// two warps per SM sub-partition overlap to ~21 cycles per DMMA (the pipe's 16 = 76 % busy).
 __device__ __forceinline__ double cvt_u8(unsigned v)
 {
-#if SQW_PACKED_CVT_MAGIC
-    return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
-#else
     return __uint2double_rn(v);
-#endif
 }
 
-template <int NCT>
+// DW = DMMA warps per CTA (8: one CTA per SM, 352 threads; 4: two CTAs per SM, 192 threads), NT = threads
+template <int NCT, int DW = 8, int NT = kThreads>
 struct PackedEval {
     static_assert(NCT == 1, "packed evaluation: one class tile");
-    static constexpr int NBG = kPackedNBG;
+    static constexpr int NBG = kPackedMaxGroups / DW;   // 16-column groups per DMMA warp
+    static constexpr int kDmmaWarps = DW, kWarps = NT / 32, kThreads = NT;
     const AdmmDev &P;
     int blk, cta, G;
     unsigned char *rows;
@@ -208,7 +208,7 @@ struct PackedEval {
             if (!loaded && ntiles > 0)
                 mbar_wait(&full[0], 0);
             SQW_EPROF(1)
-            const bool last_group = warp + kDmmaWarps * (NBG - 1) < ngroups;
+            const int ngw = (ngroups - warp + kDmmaWarps - 1) / kDmmaWarps;  // groups of this warp
 #pragma unroll 2
             for (int j = 0; j < ntiles; ++j) {
                 const unsigned char *rp = rows + (size_t)(kTileRows * j + gid) * rsq + 4 * qd;
@@ -224,7 +224,7 @@ struct PackedEval {
                     pa[c][0] = pa[c][1] = 0.0;
 #pragma unroll
                 for (int i = 0; i < NBG; ++i) {
-                    if (i == NBG - 1 && !last_group)  // warp-uniform: only a warp's last group can be absent
+                    if (i >= ngw)  // warp-uniform
                         break;
                     dmma884(pa[0], cvt_u8(wv[i] & 0xffu), wreg[4 * i + 0]);
                     dmma884(pa[1], cvt_u8((wv[i] >> 8) & 0xffu), wreg[4 * i + 1]);
@@ -295,71 +295,79 @@ struct PackedEval {
         __syncthreads();
         SQW_EPROF(3)
 
-        // ---------------- pass 2: G += R^T n over every tile ----------------
-        double acc[NBG][2][2];
+        // ---------------- pass 2: G += R^T n over every tile, then the mean / sd correction and
+        // the store of the CTA's partial gradient. The accumulators of HG = 6 column groups per
+        // warp live in registers; a warp with 12 groups (two CTAs per SM) makes two sweeps.
+        constexpr int HG = 6, NH = NBG / HG;
+        static_assert(NBG % HG == 0, "column groups per warp");
+        const int ngw = dmma_warp ? (ngroups - warp + kDmmaWarps - 1) / kDmmaWarps : 0;
 #pragma unroll
-        for (int i = 0; i < NBG; ++i)
+        for (int hh = 0; hh < NH; ++hh) {
+            double acc[HG][2][2];
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
-                acc[i][h][0] = acc[i][h][1] = 0.0;
-        if (dmma_warp) {
-            const bool last_group = warp + kDmmaWarps * (NBG - 1) < ngroups;
+            for (int i = 0; i < HG; ++i)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    acc[i][h][0] = acc[i][h][1] = 0.0;
+            if (dmma_warp && hh * HG < ngw) {
 #pragma unroll 2
-            for (int j = 0; j < ntiles; ++j) {
-                const double a0 = rres[(size_t)(kTileRows * j + qd) * 8 + gid];      // R[row qd][class gid]
-                const double a1 = rres[(size_t)(kTileRows * j + 4 + qd) * 8 + gid];  // R[row 4+qd][class gid]
-                const unsigned char *rp0 = rows + (size_t)(kTileRows * j + qd) * rsq + 2 * gid;
-                const unsigned char *rp1 = rp0 + 4 * (size_t)rsq;
-                unsigned x0[NBG], x1[NBG];
+                for (int j = 0; j < ntiles; ++j) {
+                    const double a0 = rres[(size_t)(kTileRows * j + qd) * 8 + gid];      // R[row qd][class gid]
+                    const double a1 = rres[(size_t)(kTileRows * j + 4 + qd) * 8 + gid];  // R[row 4+qd][class gid]
+                    const unsigned char *rp0 = rows + (size_t)(kTileRows * j + qd) * rsq + 2 * gid;
+                    const unsigned char *rp1 = rp0 + 4 * (size_t)rsq;
+                    unsigned x0[HG], x1[HG];
 #pragma unroll
-                for (int i = 0; i < NBG; ++i) {
-                    const int g = warp + kDmmaWarps * i;
-                    x0[i] = (g < ngroups) ? *reinterpret_cast<const unsigned short *>(rp0 + 16 * g) : 0u;
-                    x1[i] = (g < ngroups) ? *reinterpret_cast<const unsigned short *>(rp1 + 16 * g) : 0u;
-                }
-                // rows 0..3 of every group first, then rows 4..7: an accumulator is re-used at a
-                // distance of 2 NBG DMMAs (latency 26 cycles, issue 16)
+                    for (int i = 0; i < HG; ++i) {
+                        const int g = warp + kDmmaWarps * (hh * HG + i);
+                        x0[i] = (g < ngroups) ? *reinterpret_cast<const unsigned short *>(rp0 + 16 * g) : 0u;
+                        x1[i] = (g < ngroups) ? *reinterpret_cast<const unsigned short *>(rp1 + 16 * g) : 0u;
+                    }
+                    // rows 0..3 of every group first, then rows 4..7: an accumulator is re-used at a
+                    // distance of 2 HG DMMAs (latency 26 cycles, issue 16)
 #pragma unroll
-                for (int i = 0; i < NBG; ++i) {
-                    if (i == NBG - 1 && !last_group)
-                        break;
-                    dmma884(acc[i][0], a0, cvt_u8(x0[i] & 0xffu));
-                    dmma884(acc[i][1], a0, cvt_u8(x0[i] >> 8));
-                }
+                    for (int i = 0; i < HG; ++i) {
+                        if (hh * HG + i >= ngw)  // warp-uniform
+                            break;
+                        dmma884(acc[i][0], a0, cvt_u8(x0[i] & 0xffu));
+                        dmma884(acc[i][1], a0, cvt_u8(x0[i] >> 8));
+                    }
 #pragma unroll
-                for (int i = 0; i < NBG; ++i) {
-                    if (i == NBG - 1 && !last_group)
-                        break;
-                    dmma884(acc[i][0], a1, cvt_u8(x1[i] & 0xffu));
-                    dmma884(acc[i][1], a1, cvt_u8(x1[i] >> 8));
+                    for (int i = 0; i < HG; ++i) {
+                        if (hh * HG + i >= ngw)
+                            break;
+                        dmma884(acc[i][0], a1, cvt_u8(x1[i] & 0xffu));
+                        dmma884(acc[i][1], a1, cvt_u8(x1[i] >> 8));
+                    }
                 }
             }
-            // lane holds sum_i R[i][class gid] n[i][16 g + 4 qd + 2 e + h] in acc[i][h][e]; column 0
-            // (g = 0: warp 0, qd = 0, h = e = 0) is the class sum of the residuals
-            if (warp == 0 && qd == 0)
-                scr[kDmmaWarps * 8 + gid] = acc[0][0][0];
-        }
-        __syncthreads();
-        SQW_EPROF(5)
-
-        // ---------------- epilogue: mean / sd correction, partial gradient of this CTA ----------------
-        if (warp < kDmmaWarps && gid < P.C) {
-            const double sc = scr[kDmmaWarps * 8 + gid];
-            double *gp = P.gpart + ((size_t)blk * P.Gmax + cta) * P.npad + (size_t)gid * dimp;
+            if (hh == 0) {
+                // lane holds sum_i R[i][class gid] n[i][16 g + 4 qd + 2 e + h] in acc[i][h][e]; column 0
+                // (g = 0: warp 0, qd = 0, h = e = 0) is the class sum of the residuals
+                if (warp == 0 && qd == 0)
+                    scr[kDmmaWarps * 8 + gid] = acc[0][0][0];
+                __syncthreads();
+                SQW_EPROF(5)
+            }
+            // mean / sd correction, partial gradient of this CTA
+            if (dmma_warp && gid < P.C) {
+                const double sc = scr[kDmmaWarps * 8 + gid];
+                double *gp = P.gpart + ((size_t)blk * P.Gmax + cta) * P.npad + (size_t)gid * dimp;
 #pragma unroll
-            for (int i = 0; i < NBG; ++i) {
-                const int g = warp + kDmmaWarps * i;
-                const int col = 16 * g + 4 * qd;
-                if (g < ngroups) {
-                    const double2 s01 = *reinterpret_cast<const double2 *>(sinvsd + col);
-                    const double2 s23 = *reinterpret_cast<const double2 *>(sinvsd + col + 2);
-                    const double2 m01 = *reinterpret_cast<const double2 *>(smean + col);
-                    const double2 m23 = *reinterpret_cast<const double2 *>(smean + col + 2);
-                    double2 *dst = reinterpret_cast<double2 *>(gp + col);
-                    __stcg(dst, make_double2((acc[i][0][0] - m01.x * sc) * s01.x,
-                                             (acc[i][1][0] - m01.y * sc) * s01.y));
-                    __stcg(dst + 1, make_double2((acc[i][0][1] - m23.x * sc) * s23.x,
-                                                 (acc[i][1][1] - m23.y * sc) * s23.y));
+                for (int i = 0; i < HG; ++i) {
+                    const int g = warp + kDmmaWarps * (hh * HG + i);
+                    const int col = 16 * g + 4 * qd;
+                    if (g < ngroups) {
+                        const double2 s01 = *reinterpret_cast<const double2 *>(sinvsd + col);
+                        const double2 s23 = *reinterpret_cast<const double2 *>(sinvsd + col + 2);
+                        const double2 m01 = *reinterpret_cast<const double2 *>(smean + col);
+                        const double2 m23 = *reinterpret_cast<const double2 *>(smean + col + 2);
+                        double2 *dst = reinterpret_cast<double2 *>(gp + col);
+                        __stcg(dst, make_double2((acc[i][0][0] - m01.x * sc) * s01.x,
+                                                 (acc[i][1][0] - m01.y * sc) * s01.y));
+                        __stcg(dst + 1, make_double2((acc[i][0][1] - m23.x * sc) * s23.x,
+                                                     (acc[i][1][1] - m23.y * sc) * s23.y));
+                    }
                 }
             }
         }

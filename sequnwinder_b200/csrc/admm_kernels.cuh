@@ -41,6 +41,9 @@ __device__ __forceinline__ int ld_volatile_int(const int *p)
 //   MODE 2  the same with W read from global memory (row lengths beyond shared memory).
 //   MODE 8  the CTA's rows as byte counts resident in shared memory, three bulk phases per
 //           evaluation (PackedEval): count matrices with rows up to 768 columns and C <= 8.
+//   MODE 9  MODE 8 with two CTAs of 192 threads per SM (4 DMMA + 2 helper warps each): the CTAs of
+//           an SM belong to different ADMM blocks, so one evaluates while the other sits in its
+//           solver's exchange chain.
 template <int NCT, int MODE>
 struct StreamEval {
     const AdmmDev &P;
@@ -77,7 +80,11 @@ struct EvalSelect<NCT, 5> {   // MODE 4 with 21 k-steps per DMMA warp (rows <= 6
 };
 template <int NCT>
 struct EvalSelect<NCT, 8> {   // packed counts resident in shared memory (admm_eval_packed.cuh)
-    typedef PackedEval<NCT> type;
+    typedef PackedEval<NCT, 8, kThreads> type;
+};
+template <int NCT>
+struct EvalSelect<NCT, 9> {   // the same with two CTAs of 192 threads per SM
+    typedef PackedEval<NCT, ModeCfg<9>::DW, ModeCfg<9>::NT> type;
 };
 
 // Shared-memory copy of the (tiny) leaf -> edge -> parent tables: the augmented term of every
@@ -247,9 +254,11 @@ struct BlockProblem {
 // cfg-2; with a fixed partition 39 % of the SM time was idle). The re-grouping points depend only
 // on evaluation counts, never on timing, so results stay reproducible run to run.
 template <int NCT, int MODE>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(ModeCfg<MODE>::NT, ModeCfg<MODE>::MINB)
 admm_xupdate_kernel(AdmmDev P, TileSmemLayout L, int phase, int eval_cap)
 {
+    constexpr int kThreads = ModeCfg<MODE>::NT;   // (shadows the namespace constant: this kernel's CTA size)
+    constexpr int kCap = (MODE == 9) ? kPackedSliceCap2 : kSliceCap;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ SolveSmem sm;
     __shared__ int s_blk, s_G;
@@ -325,6 +334,16 @@ admm_xupdate_kernel(AdmmDev P, TileSmemLayout L, int phase, int eval_cap)
     }
 
     GroupBarrier gb{P.bar + ((size_t)phase * P.T_local + blk) * 32, 0u, G};
+    if (MODE == 9 && P.skew_ns > 0 && (int)blockIdx.x - cta >= P.n_sm - G / 2) {
+        // Two CTAs per SM only pay when the two evaluate at DIFFERENT times: the CTAs of the second
+        // wave (block indices past the number of SMs share an SM with one of the first wave) start
+        // half a trip late, after which the pairs stay in anti-phase - one in its evaluation
+        // (DMMA pipe), the other in its solver's exchange chain (latency). Left alone, all blocks
+        // start together and stay in step, each evaluation taking twice as long.
+        const long long t_end = sqw_now_ns() + P.skew_ns;
+        while (sqw_now_ns() < t_end)
+            __nanosleep(500);
+    }
     __syncthreads();
 #if SQW_AUG_CACHE
     if (!resume)
@@ -345,13 +364,13 @@ admm_xupdate_kernel(AdmmDev P, TileSmemLayout L, int phase, int eval_cap)
     ws.cta = cta;
     ws.prof = P.prof ? s_prof : nullptr;
     // modes 4/5 keep W in registers: the head of the dynamic shared memory is the slice cache
-    ws.slice = ((MODE == 4 || MODE == 5 || MODE == 8) && NCT == 1) ? reinterpret_cast<double *>(smem_raw)
-                                                                  : nullptr;
+    ws.slice = ((MODE == 4 || MODE == 5 || MODE == 8 || MODE == 9) && NCT == 1)
+                   ? reinterpret_cast<double *>(smem_raw) : nullptr;
     int status = 0;
     bool finished = false;
     const long long t_loop0 = (P.prof && threadIdx.x == 0) ? sqw_now_ns() : 0;
-    const int evals = lbfgs_group_solve(prob, ws, gb, sm, 0.1, 10e-16, status, eval_cap, resume,
-                                        &finished);  // eps, xtol: LOne.java:874-875
+    const int evals = lbfgs_group_solve<BlockProblem<Eval>, kThreads, kCap>(
+        prob, ws, gb, sm, 0.1, 10e-16, status, eval_cap, resume, &finished);  // eps, xtol: LOne.java:874-875
     const long long t_loop1 = (P.prof && threadIdx.x == 0) ? sqw_now_ns() : 0;
     ev.drain();
     if (P.prof && threadIdx.x == 0) {
@@ -836,9 +855,10 @@ admm_packed_stats_kernel(const double *mean, const double *sd, const int *col_id
 // ------------------------------------------------------------------ test kernels
 // One evaluation per local block at the current x_t with the device's z / u_t / sm_x state.
 template <int NCT, int MODE>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(ModeCfg<MODE>::NT, ModeCfg<MODE>::MINB)
 admm_eval_kernel(AdmmDev P, TileSmemLayout L, double pho, double *f_out)
 {
+    constexpr int kThreads = ModeCfg<MODE>::NT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ SolveSmem sm;
     const int blk = blockIdx.x / P.G, cta = blockIdx.x - blk * P.G;
@@ -850,7 +870,7 @@ admm_eval_kernel(AdmmDev P, TileSmemLayout L, double pho, double *f_out)
     BlockProblem<Eval> prob{P, blk, cta, P.G, pho, P.ut + (size_t)blk * P.upad, ev,
                             P.leaf_edge_ptr, P.edge_par};
     double fpart = prob.eval_partial(xt);
-    if (MODE == 4 || MODE == 5 || MODE == 6 || MODE == 8) {
+    if (MODE == 4 || MODE == 5 || MODE == 6 || MODE == 8 || MODE == 9) {
         // further evaluations exercise the ring wrap-around / resident path; results must agree
         for (int rep = 0; rep < 2; ++rep) {
             __syncthreads();
@@ -859,7 +879,7 @@ admm_eval_kernel(AdmmDev P, TileSmemLayout L, double pho, double *f_out)
                 fpart = nan("");
         }
     }
-    fpart = block_sum(fpart, sm.red);
+    fpart = block_sum<kThreads / 32>(fpart, sm.red);
     ev.drain();
     gb.sync();
     const int n = P.npad;
@@ -868,7 +888,7 @@ admm_eval_kernel(AdmmDev P, TileSmemLayout L, double pho, double *f_out)
     double faug = 0.0;
     for (int k = k0 + threadIdx.x; k < k1; k += kThreads)
         P.g[(size_t)blk * n + k] = prob.grad_coord(k, __ldcg(xt + k), faug);
-    const double fa = block_sum(faug, sm.red);
+    const double fa = block_sum<kThreads / 32>(faug, sm.red);
     if (threadIdx.x == 0)
         atomicAdd(f_out + blk, fpart + fa);
 }

@@ -539,7 +539,7 @@ struct SolveWs {
     double *spart; // [G][kNumDots]
     int G, cta;
     long long *prof; // optional (shared memory): ns in E, barrier1, R, barrier2, S, U, barrier3, evals, ...
-    double *slice;   // optional shared memory, kSliceVectors * kSliceCap doubles: the CTA's coordinate
+    double *slice;   // optional shared memory, kSliceVectors * CAP doubles: the CTA's coordinate
                      // slice of x, d, g_old, wa, S, Y stays on chip for the whole launch
 };
 
@@ -612,7 +612,7 @@ struct CoordRegs {
     double s[kLbfgsM], y[kLbfgsM];
 };
 
-template <class Problem>
+template <class Problem, int NT = kThreads, int CAP = kSliceCap>
 __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier &gb,
                                  SolveSmem &sm, double eps, double xtol, int &status,
                                  int eval_cap = 0x7fffffff, bool resume = false,
@@ -627,15 +627,15 @@ __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier 
     const bool mine = kf < k1;
     LbState &st = sm.st;
     if (!resume) {
-        for (int i = threadIdx.x; i < (int)(sizeof(LbState) / sizeof(int)); i += kThreads)
+        for (int i = threadIdx.x; i < (int)(sizeof(LbState) / sizeof(int)); i += NT)
             reinterpret_cast<int *>(&st)[i] = 0;
     }
-    // slice cache: thread t owns slot t of every vector (kSliceCap < kThreads: one coordinate each)
-    static_assert(kSliceCap <= kThreads, "one slice coordinate per thread");
-    const bool cached = ws.slice != nullptr && k1 - k0 <= kSliceCap;
-    double *const cx = ws.slice + threadIdx.x;             // + v * kSliceCap: vector v
-    double *const cd = cx + kSliceCap, *const cgo = cx + 2 * kSliceCap, *const cwa = cx + 3 * kSliceCap;
-    double *const cS = cx + 4 * kSliceCap, *const cY = cx + (4 + kLbfgsM) * kSliceCap;
+    // slice cache: thread t owns slot t of every vector (CAP <= NT: one coordinate each)
+    static_assert(CAP <= NT, "one slice coordinate per thread");
+    const bool cached = ws.slice != nullptr && k1 - k0 <= CAP;
+    double *const cx = ws.slice + threadIdx.x;             // + v * CAP: vector v
+    double *const cd = cx + CAP, *const cgo = cx + 2 * CAP, *const cwa = cx + 3 * CAP;
+    double *const cS = cx + 4 * CAP, *const cY = cx + (4 + kLbfgsM) * CAP;
     if (cached && mine) {
         *cx = __ldcg(ws.x + kf);
         if (resume) {
@@ -644,8 +644,8 @@ __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier 
             *cwa = ws.wa[kf];
 #pragma unroll
             for (int i = 0; i < kLbfgsM; ++i) {
-                cS[i * kSliceCap] = ws.S[(size_t)i * n + kf];
-                cY[i * kSliceCap] = ws.Y[(size_t)i * n + kf];
+                cS[i * CAP] = ws.S[(size_t)i * n + kf];
+                cY[i * CAP] = ws.Y[(size_t)i * n + kf];
             }
         }
     }
@@ -653,14 +653,14 @@ __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier 
     // read once per launch; naug = number of cached edges of this thread's coordinate, -1 = not cached
     int naug = -1;
 #if SQW_AUG_CACHE
-    double *const caug = cx + kSliceVectors * kSliceCap;
+    double *const caug = cx + kSliceVectors * CAP;
     if (cached && mine) {
         double a[6];
         int ne = 0;
         if (prob.aug_load(kf, a, ne)) {
 #pragma unroll
             for (int j = 0; j < 6; ++j)
-                caug[j * kSliceCap] = a[j];
+                caug[j * CAP] = a[j];
             naug = ne;
         }
     }
@@ -688,8 +688,8 @@ __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier 
 #pragma unroll
                 for (int i = 0; i < kLbfgsM; ++i) {
                     if ((valid >> i) & 1u) {
-                        c.s[i] = cS[i * kSliceCap];
-                        c.y[i] = cY[i * kSliceCap];
+                        c.s[i] = cS[i * CAP];
+                        c.y[i] = cY[i * CAP];
                     }
                 }
             }
@@ -714,7 +714,7 @@ __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier 
             double a[6];
 #pragma unroll
             for (int j = 0; j < 6; ++j)
-                a[j] = caug[j * kSliceCap];
+                a[j] = caug[j * CAP];
             c.gaug = prob.aug_term_cached(c.x, a, naug, c.faug);
             return;
         }
@@ -806,7 +806,7 @@ __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier 
             if (!cached)
                 ws.g[kf] = g0;
         }
-        for (int k = kf + kThreads; k < k1; k += kThreads) {  // (never with the slice cache)
+        for (int k = kf + NT; k < k1; k += NT) {  // (never with the slice cache)
             CoordRegs c;
             double v[Problem::kBatch], gk, yn;
             prob.data_issue(k, v);
@@ -824,7 +824,7 @@ __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier 
         if (warp == 0) {
             double acc = 0.0;
 #pragma unroll
-            for (int w = 0; w < kWarps; ++w)
+            for (int w = 0; w < NT / 32; ++w)
                 acc += sm.wred[w][lane];
             __stcg(ws.spart + (size_t)cta * kNumDots + lane, acc);
         }
@@ -878,7 +878,7 @@ __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier 
                 if (cached)
                     *cx = xn;
             }
-            for (int k = kf + kThreads; k < k1; k += kThreads)
+            for (int k = kf + NT; k < k1; k += NT)
                 ws.x[k] = ws.wa[k] + dec.stp * ws.d[k];
         } else {  // ACT_NEWDIR
             if (mine) {
@@ -888,8 +888,8 @@ __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier 
                 if (dec.slot >= 0) {
                     ws.S[(size_t)dec.slot * n + kf] = snew;
                     if (cached) {
-                        cS[dec.slot * kSliceCap] = snew;
-                        cY[dec.slot * kSliceCap] = yn0;
+                        cS[dec.slot * CAP] = snew;
+                        cY[dec.slot * CAP] = yn0;
                     }
                 }
                 double dn = dec.cg * g0;
@@ -912,7 +912,7 @@ __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier 
                     *cx = xn;
                 }
             }
-            for (int k = kf + kThreads; k < k1; k += kThreads) {
+            for (int k = kf + NT; k < k1; k += NT) {
                 const double gk = ws.g[k];
                 if (dec.slot >= 0)
                     ws.S[(size_t)dec.slot * n + k] = dec.stp_accept * ws.d[k];

@@ -18,6 +18,18 @@ constexpr int kLbfgsM = 5;        // L-BFGS history length (LOne.java:868)
 constexpr int kThreads = 352;     // threads per CTA of the x-update kernel: 8 DMMA + 2 softmax +
                                   // 1 producer warp; 65536 / 352 leaves 184 registers per thread
 constexpr int kWarps = kThreads / 32;
+// Per evaluation mode: threads per CTA, CTAs per SM the kernel is built for, DMMA warps per CTA.
+// MODE 9 is the packed-count path with TWO CTAs per SM (192 threads: 4 DMMA + 2 helper warps, the
+// same 168 registers per thread): while one CTA of an SM sits in the solver's exchange chain
+// (latency bound, the DMMA pipe idle) the other one evaluates.
+template <int MODE>
+struct ModeCfg {
+    static constexpr int NT = kThreads, MINB = 1, DW = 8;
+};
+template <>
+struct ModeCfg<9> {
+    static constexpr int NT = 192, MINB = 2, DW = 4;
+};
 constexpr int kProfSlots = 32;  // SQW_ADMM_PROFILE counters per CTA
 constexpr int kNumDots = 32;      // scalar partials exchanged per evaluation (see admm_solver.cuh)
 constexpr int kMaxEdgesPerLeaf = 32;
@@ -71,6 +83,8 @@ struct AdmmDev {
     int upad;       // E * dimp
     int wstride;    // row stride of W in shared memory (bank-conflict free)
     int world;      // ranks
+    int n_sm;       // SMs of the device (MODE 9: CTAs with blockIdx >= n_sm are an SM's second CTA)
+    int skew_ns;    // MODE 9: start delay of the second-wave blocks (0 = none)
     double ridge;   // lambda
 
     // ---- training data, block-major ----

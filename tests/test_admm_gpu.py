@@ -395,7 +395,7 @@ def test_full_cfg2_tracks_oracle_like_a_one_ulp_perturbation(cfg2_full, cfg2_con
     for k in (1, 2, 3):
         xo, tr, ctrl_err, ctrl_same = cfg2_controls[k]
         lo = run_gpu(p, T, k, 1, packed=packed)
-        assert (lo.stats.eval_mode == 8) == packed
+        assert (lo.stats.eval_mode in (8, 9)) == packed
         err = _rel(lo.getX(), xo)
         same = np.array_equal(lo.log.nfev, tr.log_nfev[:, order])
         print(f"cfg2 full ({'packed' if packed else 'fp64'}), {k} ADMM iterations: device vs oracle "
@@ -478,14 +478,18 @@ def test_packed_evaluation_matches_oracle(oracle, cfg, n, mf, T):
     ("cfg1", 2000, None, 5, 5, 1),
     ("cfg2", 4000, None, 8, 4, 1),
     ("cfg1", 301, 24, 7, 8, 2),
-    ("cfg2", 20000, None, 8, 1, 1),     # the benchmark's shape: 144 rows per CTA resident
+    ("cfg2", 20000, None, 8, 1, 1),     # the benchmark's shape: 72 (MODE 9) / 144 (MODE 8) rows per CTA resident
 ])
-def test_packed_trainer_matches_oracle_fixed_iterations(oracle, cfg, n, mf, T, A, S):
+@pytest.mark.parametrize("two_ctas_per_sm", [False, True])
+def test_packed_trainer_matches_oracle_fixed_iterations(oracle, monkeypatch, cfg, n, mf, T, A, S, two_ctas_per_sm):
     p = make_problem(cfg, n, max_features=mf)
     xo, smo, tr = oracle.lone_execute(p.x0, p.smx0, p.data, p.cls, p.weights, p.st, p.num_classes,
                                       num_threads=T, admm_max_itr=A, nodes_max_itr=S, host_threads=8)
+    if two_ctas_per_sm:
+        monkeypatch.setenv("SQW_ADMM_PACKED_MODE", "9")
     lo = run_gpu(p, T, A, S, packed=True)
-    assert lo.stats.eval_mode == 8                                   # the packed kernels ran
+    # the packed kernels ran: MODE 8 (one CTA per SM), or the opt-in MODE 9 (two CTAs per SM)
+    assert lo.stats.eval_mode == (9 if two_ctas_per_sm else 8)
     xg, smg = lo.getX(), lo.getsmX()
     assert lo.stats.outer_iters == tr.outer_iters
     assert lo.log.admm_iters == tr.admm_iters
@@ -508,7 +512,7 @@ def test_counts_outside_the_packed_kernels_are_expanded_on_the_device(oracle):
     xo, smo, tr = oracle.lone_execute(p.x0, p.smx0, p.data, p.cls, p.weights, p.st, p.num_classes,
                                       num_threads=T, admm_max_itr=A, nodes_max_itr=S, host_threads=8)
     lo = run_gpu(p, T, A, S, packed=True)
-    assert lo.stats.eval_mode != 8
+    assert lo.stats.eval_mode not in (8, 9)
     assert np.array_equal(lo.log.nfev, tr.log_nfev[:, opt.java_block_order(T)])
     assert np.abs(lo.getX() - xo).max() <= REL_TOL * np.abs(xo).max()
     assert np.abs(lo.getsmX() - smo).max() <= REL_TOL * np.abs(smo).max()
@@ -526,7 +530,7 @@ def test_packed_ridge_sweep_and_resident_reuse(oracle):
     base.setPho(1.7); base.set_numThreads(5); base.initUandZ()
     out = base.sweep(ridges)
     for lam, (x, smx, stats, log) in zip(ridges, out):
-        assert stats.eval_mode == 8
+        assert stats.eval_mode in (8, 9)
         fresh = run_gpu(p, 5, 6, 2, ridge=lam, packed=True)
         assert np.array_equal(x, fresh.getX()) and np.array_equal(smx, fresh.getsmX())
         xo, _, _ = oracle.lone_execute(p.x0, p.smx0, p.data, p.cls, p.weights, p.st, p.num_classes,

@@ -103,7 +103,7 @@ def test_resident_pipeline_sequences_to_predictions(oracle):
     st2 = _lib.AdmmStats()
     _lib.check(lib.sqw_admm_get_stats(h2, C_.byref(st2)))
     lib.sqw_admm_destroy(h2)
-    assert st2.eval_mode == 8
+    assert st2.eval_mode in (8, 9)
     assert np.abs(x2 - xo).max() <= 1e-6 * np.abs(xo).max()
     assert np.abs(smx2 - smo).max() <= 1e-6 * np.abs(smo).max()
     par = clf.destandardize(x, C, dim, hp.mean, hp.sd)
