@@ -224,7 +224,7 @@ struct PackedEval {
                     pa[c][0] = pa[c][1] = 0.0;
 #pragma unroll
                 for (int i = 0; i < NBG; ++i) {
-                    if (i >= ngw)  // warp-uniform
+                    if (i >= NBG - 2 && i >= ngw)  // warp-uniform; an absent earlier group multiplies zeros
                         break;
                     dmma884(pa[0], cvt_u8(wv[i] & 0xffu), wreg[4 * i + 0]);
                     dmma884(pa[1], cvt_u8((wv[i] >> 8) & 0xffu), wreg[4 * i + 1]);
@@ -327,14 +327,14 @@ struct PackedEval {
                     // distance of 2 HG DMMAs (latency 26 cycles, issue 16)
 #pragma unroll
                     for (int i = 0; i < HG; ++i) {
-                        if (hh * HG + i >= ngw)  // warp-uniform
+                        if (hh * HG + i >= NBG - 2 && hh * HG + i >= ngw)  // warp-uniform
                             break;
                         dmma884(acc[i][0], a0, cvt_u8(x0[i] & 0xffu));
                         dmma884(acc[i][1], a0, cvt_u8(x0[i] >> 8));
                     }
 #pragma unroll
                     for (int i = 0; i < HG; ++i) {
-                        if (hh * HG + i >= ngw)
+                        if (hh * HG + i >= NBG - 2 && hh * HG + i >= ngw)
                             break;
                         dmma884(acc[i][0], a1, cvt_u8(x1[i] & 0xffu));
                         dmma884(acc[i][1], a1, cvt_u8(x1[i] >> 8));
