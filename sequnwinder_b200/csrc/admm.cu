@@ -366,7 +366,7 @@ static int prepare(sqw_admm *h)
     TRY(h->dalloc(&D.nfev, TL));
     if (getenv("SQW_ADMM_PROFILE"))
         TRY(h->dalloc(&D.prof, (size_t)D.Gmax * kProfSlots * kNumPhases));
-    TRY(h->dalloc(&D.sum1, (size_t)D.npad + D.upad));
+    TRY(h->dalloc(&D.sum1, (size_t)2 * D.npad + D.upad));
     TRY(h->dalloc(&D.sum2, (size_t)D.E));
     TRY(h->dalloc(&D.edge_stats, (size_t)D.E * 4));
     TRY(h->dalloc(&D.leaf_xnorm, (size_t)D.C));
@@ -465,7 +465,7 @@ static int enqueue_iteration(sqw_admm *h, int slot)
     SQW_CUDA_CHECK(cudaEventRecord(h->ev_x1[slot], h->stream));
     if (h->world == 1 && !h->unfused_tail) {
         // single GPU: pack + consensus + decide in one launch (admm_consensus_fused_kernel)
-        admm_consensus_fused_kernel<<<D.E, kThreads, 0, h->stream>>>(D);
+        admm_consensus_fused_kernel<1><<<D.E, kThreads, 0, h->stream>>>(D);
         SQW_CUDA_CHECK(cudaMemcpyAsync(&h->h_ring[slot], D.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost,
                                        h->stream));
         SQW_CUDA_CHECK(cudaEventRecord(h->ev_snap[slot], h->stream));
@@ -473,8 +473,29 @@ static int enqueue_iteration(sqw_admm *h, int slot)
         h->stats.launches += 2;
         return SQW_OK;
     }
+    if (h->world > 1 && !h->unfused_tail) {
+        // multi-GPU: ONE collective per iteration. pack writes [sum x_t | sum u_t | sum x_t^2], the
+        // all-reduce makes them the sums over all T blocks, and one launch does consensus + residuals
+        // (from the sums alone) + decision
+        const int total3 = 2 * D.npad + D.upad;
+        admm_pack_kernel<true><<<(total3 + 255) / 256, 256, 0, h->stream>>>(D);
+        if (h->tail_prof) cudaEventRecord(h->ev_tail[slot][0], h->stream);
+        if ((rc = nccl_allreduce(h, D.sum1, (size_t)total3)) != SQW_OK)
+            return rc;
+        if (h->tail_prof) cudaEventRecord(h->ev_tail[slot][1], h->stream);
+        admm_consensus_fused_kernel<2><<<D.E, kThreads, 0, h->stream>>>(D);
+        if (h->tail_prof)
+            for (int j = 2; j < 5; ++j)
+                cudaEventRecord(h->ev_tail[slot][j], h->stream);
+        SQW_CUDA_CHECK(cudaMemcpyAsync(&h->h_ring[slot], D.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost,
+                                       h->stream));
+        SQW_CUDA_CHECK(cudaEventRecord(h->ev_snap[slot], h->stream));
+        SQW_CUDA_CHECK(cudaGetLastError());
+        h->stats.launches += 3;
+        return SQW_OK;
+    }
     const int total = D.npad + D.upad;
-    admm_pack_kernel<<<(total + 255) / 256, 256, 0, h->stream>>>(D);
+    admm_pack_kernel<false><<<(total + 255) / 256, 256, 0, h->stream>>>(D);
     if (h->tail_prof) cudaEventRecord(h->ev_tail[slot][0], h->stream);
     if ((rc = nccl_allreduce(h, D.sum1, (size_t)total)) != SQW_OK)
         return rc;

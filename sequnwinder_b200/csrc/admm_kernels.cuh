@@ -401,19 +401,27 @@ admm_xupdate_kernel(AdmmDev P, TileSmemLayout L, int phase, int eval_cap)
 }
 
 // ------------------------------------------------------------------ pack: sum over local blocks
+// WITH_SQ: a third section sum_t x_t^2 per coordinate, so that the primal residual of the NEW z
+// can be formed from all-reduced sums alone (one collective per iteration, see consensus_edge).
+template <bool WITH_SQ>
 __global__ void __launch_bounds__(256) admm_pack_kernel(AdmmDev P)
 {
     if (ld_volatile_int(&P.ctrl->done) || ld_volatile_int(&P.ctrl->fatal))
         return;
-    const int total = P.npad + P.upad;
+    const int total = P.npad + P.upad + (WITH_SQ ? P.npad : 0);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         double s = 0.0;
         if (i < P.npad) {
             for (int b = 0; b < P.T_local; ++b)  // local blocks are stored in summation order
                 s += P.xt[(size_t)b * P.Cp * P.dimp + i];
-        } else {
+        } else if (i < P.npad + P.upad) {
             for (int b = 0; b < P.T_local; ++b)
                 s += P.ut[(size_t)b * P.upad + (i - P.npad)];
+        } else {
+            for (int b = 0; b < P.T_local; ++b) {
+                const double v = P.xt[(size_t)b * P.Cp * P.dimp + (i - P.npad - P.upad)];
+                s += v * v;
+            }
         }
         P.sum1[i] = s;
     }
@@ -425,9 +433,18 @@ __global__ void __launch_bounds__(256) admm_pack_kernel(AdmmDev P)
 // edge, :504), xnorm, dual residual term, and this rank's part of the primal residual term.
 // FUSED: the sums over the local blocks are formed here (same order as admm_pack_kernel) instead
 // of being read from sum1 - the single-GPU path, where no all-reduce sits between pack and consensus.
-template <bool FUSED>
+// MODE_ = 0: sums from sum1 (all-reduced), primal residual of this rank's blocks (a second
+//            all-reduce of sum2 follows);
+//         1: FUSED above (single GPU);
+//         2: sums AND the whole job's primal residual from the all-reduced sum1, which then also
+//            carries sum_t x_t^2: sum_t (x_t - a)^2 = sum_t x_t^2 - 2 a sum_t x_t + T a^2 with
+//            a = z_new + sm_x[par]. One collective per ADMM iteration. The expansion cancels when
+//            the blocks agree (x_t ~ a); the residual it feeds is compared with a tolerance of
+//            1e-2 relative, the cancellation error is ~1e-12 of it (test_one_collective_tail...).
+template <int MODE_>
 __device__ __forceinline__ void consensus_edge(const AdmmDev &P, double *red)
 {
+    constexpr bool FUSED = MODE_ == 1;
     const int e = blockIdx.x;
     const int leaf = P.edge_leaf[e], par = P.edge_par[e];
     const bool first_edge = (P.leaf_edge_ptr[leaf] == e);
@@ -472,9 +489,14 @@ __device__ __forceinline__ void consensus_edge(const AdmmDev &P, double *red)
         zn2 += (par >= 0) ? zn * zn : ub * ub;
         const double dd = pho * (zn - zo);
         du2 += dd * dd;
-        for (int b = 0; b < P.T_local; ++b) {
-            const double r = P.xt[(size_t)b * P.Cp * P.dimp + xo] - zn - smp;
-            pr2 += r * r;
+        if (MODE_ == 2) {
+            const double a = zn + smp;
+            pr2 += (P.sum1[P.npad + P.upad + xo] - 2.0 * a * sx) + Td * a * a;
+        } else {
+            for (int b = 0; b < P.T_local; ++b) {
+                const double r = P.xt[(size_t)b * P.Cp * P.dimp + xo] - zn - smp;
+                pr2 += r * r;
+            }
         }
     }
     zn2 = block_sum(zn2, red);
@@ -497,7 +519,7 @@ __global__ void __launch_bounds__(kThreads) admm_consensus_kernel(AdmmDev P)
     __shared__ double red[kWarps];
     if (ld_volatile_int(&P.ctrl->done) || ld_volatile_int(&P.ctrl->fatal))
         return;
-    consensus_edge<false>(P, red);
+    consensus_edge<0>(P, red);
 }
 
 // ------------------------------------------------------------------ decide
@@ -558,7 +580,7 @@ __device__ void decide_cta(const AdmmDev &P)
         const int e0 = lep[leaf], e1 = lep[leaf + 1];
         const double xnorm = sqrt(lxn[leaf]);
         for (int e = e0; e < e1; ++e) {
-            r_t += sum2[e];
+            r_t += fmax(sum2[e], 0.0);   // (the one-collective expansion can round below zero)
             s_t += stats[e * 4 + 1];
             s_t = sqrt(s_t * P.T);
             const double primal = sqrt(r_t), dual = s_t;
@@ -643,13 +665,16 @@ __global__ void __launch_bounds__(kDecideThreads) admm_decide_kernel(AdmmDev P)
 // Single-GPU iteration tail in ONE launch: pack + consensus per edge, and the CTA that finishes
 // last (ticket counter in Ctrl) runs the decision. Same arithmetic in the same order as the three
 // kernels above, two launches and their gaps less per ADMM iteration.
+// MODE_ 1: single GPU (sums over the local blocks formed here); MODE_ 2: multi-GPU after ONE
+// all-reduce of [sum x_t | sum u_t | sum x_t^2].
+template <int MODE_>
 __global__ void __launch_bounds__(kThreads) admm_consensus_fused_kernel(AdmmDev P)
 {
     __shared__ double red[kWarps];
     __shared__ int s_last;
     if (ld_volatile_int(&P.ctrl->done) || ld_volatile_int(&P.ctrl->fatal))
         return;
-    consensus_edge<true>(P, red);
+    consensus_edge<MODE_>(P, red);
     if (threadIdx.x == 0) {
         __threadfence();  // this edge's statistics before the ticket
         const unsigned t = atomicAdd(&P.ctrl->cons_count, 1u);
