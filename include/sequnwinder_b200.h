@@ -33,6 +33,19 @@ extern "C" {
 
 #define SQW_ABI_VERSION 2
 
+/* Environment hooks read by the library (none is needed in production; defaults in brackets):
+ *   tests      SQW_ADMM_EVAL_MODE=1|2|6   force a more general fp64 evaluation path
+ *              SQW_ADMM_NO_PACKED=1       count matrices always through the fp64 kernels
+ *              SQW_ADMM_PACKED_MODE=9     packed counts with two CTAs per SM (built, measured slower)
+ *              SQW_ADMM_UNFUSED=1         iteration tail as separate kernels / two collectives
+ *   profiling  SQW_ADMM_PROFILE=1         per-phase timers of the x-update kernel on stderr
+ *              SQW_ADMM_TAIL_PROFILE=1    multi-GPU: events between the kernels of the iteration tail
+ *   tuning     SQW_ADMM_CAPS=a,b,c,d,e    evaluation caps of the x-update phases [8,12,16,20,26]
+ *              SQW_ADMM_GCAP=n            most CTAs a re-grouped block may get [~ sqrt(rows per block)]
+ *              SQW_ADMM_SKEW_NS=n         MODE 9 probe: start delay of an SM's second CTA [0]
+ *              SQW_ADMM_L2_PERSIST_MB=n   persisting-L2 window over the fp64 matrix [off]
+ *              SQW_KMER_WARP64=1          the older 64-bit warp kernel of path 1
+ * (SQW_LIB_PATH, read by the Python mirror only, selects another build of this library for A/B runs.) */
 int sqw_abi_version(void);
 const char *sqw_last_error(void);
 /* number of visible CUDA devices (0 when there is none); never fails */

@@ -109,3 +109,56 @@ def test_local_blocks_errors():
     with pytest.raises(ValueError):
         parallel.local_blocks(2, 3, 4)      # rank 3 of 4 owns nothing when T == 2
     assert parallel.block_rows(11, 3, 2) == [2, 5, 8]   # rows 9, 10 are dropped
+
+
+def test_local_row_indices_match_the_library_convention():
+    """rows_local form of sqw_admm_set_problem_counts_dev (include/sequnwinder_b200.h): a rank holds
+    the rows i < floor(N/T) T with (i mod T) mod world == rank in ascending order, so row s of block
+    t sits at local position s * T_local + t // world - the index the device gather uses."""
+    sys.path.insert(0, ROOT)
+    from sequnwinder_b200 import parallel
+    for (n, T, world) in [(103, 8, 2), (64, 8, 8), (1999999, 8, 4), (50, 5, 3), (40, 8, 1)]:
+        nb = n // T
+        seen = []
+        for rank in range(world):
+            try:
+                blocks = sorted(parallel.local_blocks(T, rank, world))
+            except ValueError:
+                assert not any(t % world == rank for t in range(T))
+                continue
+            idx = parallel.local_row_indices(n, T, rank, world)
+            assert np.all(np.diff(idx) > 0) and idx.size == nb * len(blocks)
+            TL = len(blocks)
+            for t in blocks[:3]:
+                for s_ in (0, nb // 2, nb - 1):
+                    assert idx[s_ * TL + t // world] == t + T * s_
+            seen.append(idx)
+        allrows = np.sort(np.concatenate(seen))
+        assert np.array_equal(allrows, np.arange(nb * T))          # every kept row exactly once
+
+
+def test_sharded_column_statistics_combine_to_the_global_plan():
+    """The sharded column plan (sqw_prepare_stats_dev per rank -> all-reduce min / max / sums ->
+    sqw_prepare_finish_dev): combining per-shard min / max / sum w x / sum w x^2 reproduces the
+    statistics Classifier.java:337-372 computes over all rows (host arithmetic of the same
+    combination; the device kernels are checked on the GPU)."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import make_problem
+    from sequnwinder_b200 import parallel
+    p = make_problem("cfg1", 403, max_features=None)
+    counts, w = p.counts.astype(np.float64), p.weights
+    T, world = 8, 4
+    parts = [parallel.local_row_indices(counts.shape[0], T, r, world) for r in range(world)]
+    dropped = np.arange((counts.shape[0] // T) * T, counts.shape[0])
+    parts[0] = np.concatenate([parts[0], dropped])                 # rank 0 adds the rows the blocking drops
+    mn = np.min([counts[i].min(0) for i in parts], axis=0)
+    mx = np.max([counts[i].max(0) for i in parts], axis=0)
+    swx = sum((w[i, None] * counts[i]).sum(0) for i in parts)
+    swxx = sum((w[i, None] * counts[i] ** 2).sum(0) for i in parts)
+    tot = sum(w[i].sum() for i in parts)
+    keep = np.nonzero(mn != mx)[0]
+    mean = swx / tot
+    sd = np.sqrt(np.abs(swxx - tot * mean * mean) / (tot - 1))
+    assert np.array_equal(keep, p.keep)
+    assert np.allclose(mean[keep], p.mean[1:], rtol=1e-12) and np.allclose(sd[keep], p.sd[1:], rtol=1e-11)
