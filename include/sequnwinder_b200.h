@@ -79,7 +79,9 @@ int sqw_kmer_count(const char *bases, const int64_t *offsets, int64_t n, int kmi
 
 /* Device-resident entry point: all pointers are device pointers, launch is asynchronous on
  * `stream`. max_len = longest sequence (bases). d_status: one int32, OR-ed with 1 when a
- * character outside ACGTN was met (caller zeroes it and reads it back). */
+ * character outside ACGTN was met and with 4 when a row is longer than max_len (that row is
+ * truncated to max_len; the host variant returns SQW_ERR_INVALID_ARG). The caller zeroes it and
+ * reads it back. */
 int sqw_kmer_count_dev(const uint8_t *d_bases, const int64_t *d_offsets, int64_t n,
                        int64_t max_len, int kmin, int kmax, int32_t *d_counts, uint8_t *d_has_n,
                        int32_t *d_status, void *stream);
@@ -285,8 +287,9 @@ int sqw_hills_scan(const char *bases, const int64_t *offsets, int64_t n, int kmi
                    int32_t *counts, uint8_t *has_n);
 
 /* Device-resident form: all pointers are device pointers, asynchronous on `stream`. max_len =
- * longest sequence. d_status: one int32, OR-ed with 2 for a character outside ACGTN and with 4
- * when a sequence overflowed cap (caller zeroes it and reads it back). */
+ * longest sequence. d_status: one int32, OR-ed with 2 for a character outside ACGTN, with 4 when a
+ * sequence overflowed cap and with 8 when a row is longer than max_len (truncated; caller zeroes it
+ * and reads it back). */
 int sqw_hills_scan_dev(const uint8_t *d_bases, const int64_t *d_offsets, int64_t n, int64_t max_len,
                        int kmin, int kmax, const double *d_kmer_weights, int min_m, int max_m,
                        double thresh, int mode, int32_t cap, int32_t *d_hill_start,

@@ -69,7 +69,12 @@ __global__ void __launch_bounds__(kHillsWarps * 32) hills_scan_kernel(HillsParam
     const int64_t total_warps = (int64_t)gridDim.x * kHillsWarps;
     for (int64_t r = (int64_t)blockIdx.x * kHillsWarps + warp; r < p.n; r += total_warps) {
         const int64_t beg = p.offsets[r];
-        const int len = (int)(p.offsets[r + 1] - beg);
+        int len = (int)(p.offsets[r + 1] - beg);
+        if (len > p.max_len) {   // would overrun pw[] / words: truncate and report (status value 8)
+            if (lane == 0)
+                atomicOr(p.status, 8);
+            len = p.max_len;
+        }
         if (lane == 0)
             *flag = 0;
         __syncwarp();
@@ -376,6 +381,8 @@ int sqw_hills_scan(const char *bases, const int64_t *offsets, int64_t n, int kmi
         return set_error(SQW_ERR_BAD_BASE, "Nonstandard nucleotide character encountered (not ACGTN)");
     if (status & kFlagOverflow)
         return set_error(SQW_ERR_UNSUPPORTED, "a sequence produced more than cap = %d hills", cap);
+    if (status & 8)
+        return set_error(SQW_ERR_INVALID_ARG, "a sequence is longer than max_len");
     return SQW_OK;
 }
 

@@ -42,7 +42,21 @@ struct KmerParams {
     int32_t *status;
     int rows_per_block;
     int seq_words;  // 64-bit words reserved per sequence (incl. one pad word)
+    int64_t max_len;  // the caller's bound on a row's length: the shared-memory buffers are sized from it
 };
+
+// A row longer than the caller's max_len would overrun its packed words / histogram: it is
+// truncated to max_len and status bit 2 (value 4) is raised - the host wrappers turn that into
+// SQW_ERR_INVALID_ARG, a _dev caller sees it in its status word.
+constexpr int kStatusTooLong = 4;
+__device__ __forceinline__ int64_t clamp_len(const KmerParams &p, int64_t len)
+{
+    if (len > p.max_len) {
+        atomicOr(p.status, kStatusTooLong);
+        return p.max_len;
+    }
+    return len;
+}
 
 // One window position: forward code = top 2k bits of `comb`, reverse-complement code = low 2k
 // bits of rev2_64(~comb). Target is either shared (ATOMS) or global (RED) memory.
@@ -101,7 +115,7 @@ __global__ void __launch_bounds__(256) kmer_count_smem_kernel(KmerParams p)
         __syncthreads();  // histogram zeroed / re-zeroed, flags cleared
         if (valid) {
             beg = p.offsets[row];
-            len = p.offsets[row + 1] - beg;
+            len = clamp_len(p, p.offsets[row + 1] - beg);
             pack_sequence(p.bases + beg, len, words, t, tpr, &flags[g]);
         }
         __syncthreads();
@@ -157,7 +171,7 @@ __global__ void __launch_bounds__(256) kmer_count_warp_kernel(KmerParams p)
             flags[g] = 0;
         __syncwarp();
         const int64_t beg = p.offsets[row];
-        const int64_t len = p.offsets[row + 1] - beg;
+        const int64_t len = clamp_len(p, p.offsets[row + 1] - beg);
         pack_sequence(p.bases + beg, len, words, t, 32, &flags[g]);
         __syncwarp();
         const int fl = flags[g];
@@ -233,7 +247,7 @@ __global__ void __launch_bounds__(256) kmer_count_warp32_kernel(KmerParams p)
     const unsigned sh = 30u - 2u * (unsigned)(t & 15);
     for (int64_t row = (int64_t)blockIdx.x * warps + g; row < p.n; row += (int64_t)gridDim.x * warps) {
         const int64_t beg = p.offsets[row];
-        const int len = (int)(p.offsets[row + 1] - beg);
+        const int len = (int)clamp_len(p, p.offsets[row + 1] - beg);
         const uint8_t *seq = p.bases + beg;
         const int nchunks = (len + 31) >> 5;
         unsigned flags = 0;
@@ -310,7 +324,7 @@ __global__ void __launch_bounds__(256) kmer_count_global_kernel(KmerParams p)
             flags[g] = 0;
         __syncwarp();
         const int64_t beg = p.offsets[row];
-        const int64_t len = p.offsets[row + 1] - beg;
+        const int64_t len = clamp_len(p, p.offsets[row + 1] - beg);
         pack_sequence(p.bases + beg, len, words, t, 32, &flags[g]);
         __syncwarp();
         const int fl = flags[g];
@@ -390,6 +404,7 @@ static int launch_kmer(const uint8_t *d_bases, const int64_t *d_offsets, int64_t
     p.counts = d_counts;
     p.has_n = d_has_n;
     p.status = d_status;
+    p.max_len = max_len;
     p.seq_words = (int)((max_len + 31) / 32 + 1);
 
     const size_t seq_bytes = (size_t)p.seq_words * 8;
@@ -716,6 +731,8 @@ static int host_kmer_count(const char *bases, const int64_t *offsets, int64_t n,
     SQW_CUDA_CHECK(cudaMemcpy(&status, ctx.d_status, sizeof(int32_t), cudaMemcpyDeviceToHost));
     if (status & 1)
         return set_error(SQW_ERR_BAD_BASE, "Nonstandard nucleotide character encountered");
+    if (status & kStatusTooLong)
+        return set_error(SQW_ERR_INVALID_ARG, "a sequence is longer than max_len");
     return SQW_OK;
 }
 

@@ -86,3 +86,20 @@ def test_device_resident_full_size_properties():
     # host entry point agrees with the device-resident one
     host, _ = kc.count(d.bases, d.offsets)
     assert np.array_equal(host, out.cpu().numpy())
+
+
+def test_row_longer_than_max_len_is_reported_not_overrun():
+    """_dev entry point with a max_len smaller than the longest row: the row is truncated and the
+    status word says so (bit value 4); the neighbouring rows are unaffected."""
+    import torch
+    seqs = ["ACGT" * 10, "ACGTTGCA" * 40, "TTGACA" * 8]
+    kc = KmerCounter(4, 5)
+    want, _ = kc.count_sequences(seqs)
+    bases = np.frombuffer("".join(seqs).encode(), dtype=np.uint8).copy()
+    offs = np.cumsum([0] + [len(s) for s in seqs]).astype(np.int64)
+    out, has_n, status = kc.count_device(torch.from_numpy(bases).cuda(), torch.from_numpy(offs).cuda(), 64)
+    torch.cuda.synchronize()
+    assert int(status.item()) & 4
+    got = out.cpu().numpy()
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[2], want[2])
+    assert got[1].sum() == (64 - 3) + (64 - 4)                    # the truncated row: 64 bases
