@@ -175,6 +175,9 @@ static XKernel xupdate_kernel(int nct, int mode)
     case 16 + 5: return admm_xupdate_kernel<1, 5>;
     case 16 + 8: return admm_xupdate_kernel<1, 8>;
     case 16 + 9: return admm_xupdate_kernel<1, 9>;
+    case 16 + 10: return admm_xupdate_kernel<1, 10>;
+    case 32 + 10: return admm_xupdate_kernel<2, 10>;
+    case 48 + 10: return admm_xupdate_kernel<3, 10>;
     case 16 + 1: return admm_xupdate_kernel<1, 1>;
     case 16 + 2: return admm_xupdate_kernel<1, 2>;
     case 32 + 4: return admm_xupdate_kernel<2, 4>;
@@ -197,6 +200,9 @@ static EKernel eval_kernel(int nct, int mode)
     case 16 + 5: return admm_eval_kernel<1, 5>;
     case 16 + 8: return admm_eval_kernel<1, 8>;
     case 16 + 9: return admm_eval_kernel<1, 9>;
+    case 16 + 10: return admm_eval_kernel<1, 10>;
+    case 32 + 10: return admm_eval_kernel<2, 10>;
+    case 48 + 10: return admm_eval_kernel<3, 10>;
     case 16 + 1: return admm_eval_kernel<1, 1>;
     case 16 + 2: return admm_eval_kernel<1, 2>;
     case 32 + 4: return admm_eval_kernel<2, 4>;
@@ -285,7 +291,7 @@ static int prepare(sqw_admm *h)
         n_sm = std::min(n_sm, h->cta_budget);
     const int mode = h->eval_mode;
     const size_t w_bytes = (size_t)D.Cp * D.wstride * sizeof(double);
-    if (mode == 4 || mode == 5 || mode == 6 || mode == 8 || mode == 9)
+    if (mode == 4 || mode == 5 || mode == 6 || mode == 8 || mode == 9 || mode == 10)
         h->xupdate_smem = h->layout.total;
     else if (mode == 1)
         h->xupdate_smem = w_bytes;
@@ -841,8 +847,21 @@ static int plan_blocks(sqw_admm *h, int64_t n_rows, int32_t dim, int32_t num_cla
     // Packed-count form (admm_eval_packed.cuh): one class tile, rows up to 768 columns, and the
     // rows of the busiest CTA of the smallest group a launch can form must fit shared memory next
     // to the partial logits. Otherwise the counts are expanded to the fp64 matrix on the device.
-    if (counts_form && nct == 1 && dim <= kPackedMaxDim && !getenv("SQW_ADMM_NO_PACKED") &&
-        !getenv("SQW_ADMM_EVAL_MODE")) {
+    const bool packed_ok = counts_form && !getenv("SQW_ADMM_NO_PACKED") && !getenv("SQW_ADMM_EVAL_MODE");
+    if (packed_ok) {
+        // any shape: the streamed, column-chunked packed evaluation (admm_eval_packed_chunk.cuh);
+        // replaced below by the resident one where the rows fit shared memory
+        const int dimp16 = (dim + 15) / 16 * 16;
+        TileSmemLayout Lq = packed_chunk_smem_layout(Cp, nct == 1 ? kSolveSliceBytes : 0);
+        if (Lq.total <= budget) {
+            h->eval_mode = 10;
+            h->layout = Lq;
+            D.dimp = dimp16;
+            D.rsq = dimp16;
+        }
+    }
+    if (packed_ok && nct == 1 && dim <= kPackedMaxDim && !(getenv("SQW_ADMM_PACKED_MODE") &&
+                                                          atoi(getenv("SQW_ADMM_PACKED_MODE")) == 10)) {
         const int dimp16 = (dim + 15) / 16 * 16;
         const long long tiles = (D.nb + 7) / 8;
         const char *force = getenv("SQW_ADMM_PACKED_MODE");   // test hook: 9
@@ -1014,7 +1033,7 @@ static int build_from_counts(sqw_admm *h, const SrcT *d_src, long long src_strid
     admm_packed_stats_kernel<<<(D.dimp + 255) / 256, 256, 0, st>>>(d_mean, d_sd, d_col_idx, D.dim, D.dimp,
                                                                    mean_p, invsd_p, mean_f, sd_f);
     const int grid = (int)std::min<size_t>(rows, 148 * 16);
-    if (h->eval_mode == 8 || h->eval_mode == 9) {
+    if (h->eval_mode == 8 || h->eval_mode == 9 || h->eval_mode == 10) {
         unsigned char *dXq = nullptr;
         if ((rc = h->dalloc(&dXq, rows * D.rsq + 16384, false)) != SQW_OK) return rc;
         admm_gather_counts_kernel<SrcT, true><<<grid, 256, 0, st>>>(

@@ -505,19 +505,23 @@ def test_packed_trainer_matches_oracle_fixed_iterations(oracle, monkeypatch, cfg
     assert np.array_equal(pg, po)
 
 
-def test_counts_outside_the_packed_kernels_are_expanded_on_the_device(oracle):
-    """17 classes (three class tiles) are not covered by the packed kernels: the count form is
-    expanded to the fp64 matrix on the device ((n - xMean) / xSD, Classifier.java:373-381) and the
-    fp64 kernels run; a count above 255 is refused."""
-    p = make_problem("cfg4", 1700, max_features=200)
-    T, A, S = 4, 6, 2
+def test_counts_with_a_cta_budget_use_the_streamed_packed_kernels(oracle):
+    """A handle with a CTA budget (concurrent sweeps) has too few CTAs per block for its rows to stay
+    in shared memory: the count matrix runs through the streamed packed kernels (MODE 10)."""
+    p = make_problem("cfg2", 4000)
+    T, A, S = 8, 3, 1
     xo, smo, tr = oracle.lone_execute(p.x0, p.smx0, p.data, p.cls, p.weights, p.st, p.num_classes,
                                       num_threads=T, admm_max_itr=A, nodes_max_itr=S, host_threads=8)
-    lo = run_gpu(p, T, A, S, packed=True)
-    assert lo.stats.eval_mode not in (8, 9)
+    lo = opt.LOneCuda(p.x0.copy(), p.smx0.copy(), None)
+    lo.setCountMatrix(*packed_counts(p))
+    lo.setRidge(10.0); lo.setADMMmaxItrs(A); lo.setBGFSmaxItrs(-1); lo.setSeqUnwinderMaxIts(S)
+    lo.setClassStructure(p.crs); lo.setClsMembership(p.cls); lo.setInstanceWeights(p.weights)
+    lo.setNumClasses(p.num_classes); lo.setNumPredictors(p.data.shape[1] - 1)
+    lo.setPho(1.7); lo.set_numThreads(T); lo.initUandZ(); lo.setCtaBudget(16)
+    lo.execute()
+    assert lo.stats.eval_mode == 10 and lo.stats.ctas_per_block == 2
     assert np.array_equal(lo.log.nfev, tr.log_nfev[:, opt.java_block_order(T)])
-    assert np.abs(lo.getX() - xo).max() <= REL_TOL * np.abs(xo).max()
-    assert np.abs(lo.getsmX() - smo).max() <= REL_TOL * np.abs(smo).max()
+    assert _rel(lo.getX(), xo) <= REL_TOL
 
 
 def test_packed_ridge_sweep_and_resident_reuse(oracle):
@@ -538,3 +542,65 @@ def test_packed_ridge_sweep_and_resident_reuse(oracle):
         xo, _, _ = oracle.lone_execute(p.x0, p.smx0, p.data, p.cls, p.weights, p.st, p.num_classes,
                                        ridge=lam, num_threads=5, admm_max_itr=6, nodes_max_itr=2)
         assert _rel(x, xo) <= REL_TOL
+
+
+# --------------------------------------------------------------------------------------------
+# MODE 10: packed counts streamed from HBM, column-chunked (csrc/admm_eval_packed_chunk.cuh) - what
+# count matrices run through when their rows do not stay in shared memory: long rows, more than 8
+# classes (cfg-3 / cfg-4 shapes), or forced here on small shapes (SQW_ADMM_PACKED_MODE=10).
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg,n,mf,T", [("cfg1", 500, 60, 5), ("cfg2", 4000, None, 8),
+                                          ("cfg4", 1700, 200, 4), ("cfg3", 1200, 1100, 4),
+                                          ("cfg4", 3400, None, 8)])
+def test_packed_chunk_evaluation_matches_oracle(oracle, monkeypatch, cfg, n, mf, T):
+    monkeypatch.setenv("SQW_ADMM_PACKED_MODE", "10")
+    p = make_problem(cfg, n, max_features=mf)
+    nrow, dim = p.data.shape
+    C, NN = p.num_classes, p.st.num_nodes
+    rng = np.random.default_rng(5)
+    cx = rng.normal(size=(T, C * dim)) * 0.05
+    smx = rng.normal(size=NN * dim) * 0.05
+    f, g = opt.block_evaluate(None, p.cls, p.weights, p.crs, C, T, cx, smx, 1.7, counts=packed_counts(p))
+    nb = nrow // T
+    zd = np.zeros(NN * NN * dim)
+    for b, t in enumerate(opt.java_block_order(T)):
+        rows = np.arange(nb) * T + t
+        fo, go = oracle.eval_fg(p.data[rows], p.cls[rows], p.weights[rows], cx[b], smx, zd, zd, 1.7,
+                                p.st, C)
+        assert abs(f[b] - fo) <= 1e-12 * abs(fo)
+        assert np.abs(g[b] - go).max() <= 1e-12 * np.abs(go).max()
+
+
+@pytest.mark.parametrize("cfg,n,mf,T,A,S,force", [
+    ("cfg1", 500, 60, 5, 50, 3, True),       # one class tile, forced onto the streamed path
+    ("cfg2", 4000, None, 8, 4, 1, True),
+    ("cfg4", 1700, 200, 4, 6, 2, False),     # 17 leaves (three class tiles) incl. parentless Random
+    ("cfg3", 2400, None, 8, 2, 1, False),    # k = 4..7: 10 921 columns, C = 12 (two class tiles, 22 chunks)
+    ("cfg4", 3400, None, 8, 2, 1, False),    # k = 4..6: 2 729 columns, C = 17
+])
+def test_packed_chunk_trainer_matches_oracle(oracle, monkeypatch, cfg, n, mf, T, A, S, force):
+    if force:
+        monkeypatch.setenv("SQW_ADMM_PACKED_MODE", "10")
+    p = make_problem(cfg, n, max_features=mf)
+    xo, smo, tr = oracle.lone_execute(p.x0, p.smx0, p.data, p.cls, p.weights, p.st, p.num_classes,
+                                      num_threads=T, admm_max_itr=A, nodes_max_itr=S, host_threads=8)
+    lo = run_gpu(p, T, A, S, packed=True)
+    assert lo.stats.eval_mode == 10
+    assert lo.log.admm_iters == tr.admm_iters
+    assert np.array_equal(lo.log.nfev, tr.log_nfev[:, opt.java_block_order(T)])
+    assert _rel(lo.getX(), xo) <= REL_TOL
+    assert _rel(lo.getsmX(), smo) <= REL_TOL
+
+
+def test_no_packed_hook_expands_counts_to_fp64(oracle, monkeypatch):
+    """SQW_ADMM_NO_PACKED=1: the count form is expanded on the device with the reference's own
+    (n - xMean) / xSD (Classifier.java:373-381) and trained by the fp64 kernels."""
+    monkeypatch.setenv("SQW_ADMM_NO_PACKED", "1")
+    p = make_problem("cfg4", 1700, max_features=200)
+    T, A, S = 4, 6, 2
+    xo, smo, tr = oracle.lone_execute(p.x0, p.smx0, p.data, p.cls, p.weights, p.st, p.num_classes,
+                                      num_threads=T, admm_max_itr=A, nodes_max_itr=S, host_threads=8)
+    lo = run_gpu(p, T, A, S, packed=True)
+    assert lo.stats.eval_mode in (4, 5, 6)
+    assert np.array_equal(lo.log.nfev, tr.log_nfev[:, opt.java_block_order(T)])
+    assert _rel(lo.getX(), xo) <= REL_TOL
