@@ -77,6 +77,46 @@ __device__ __forceinline__ double cvt_u8(unsigned v)
 {
     return __uint2double_rn(v);
 }
+// byte t of a 32-bit word as a double: ONE I2F.F64.U8 with a byte selector (the shift folds into the
+// operand), where (w >> 8t) & 0xff through __uint2double_rn costs SHF + LOP3 + I2F.F64.U32
+__device__ __forceinline__ double cvt_byte(unsigned w, int t)
+{
+    double d;
+    asm("cvt.rn.f64.u8 %0, %1;" : "=d"(d) : "r"(w >> (8 * t)));
+    return d;
+}
+// Shared-memory operands of the DMMA loops by 32-bit shared address: ptxas folds a constant addend
+// into the instruction's immediate, so a tile needs one address per lane; the generic-pointer form
+// with a predicate per load re-derived every address from %tid (ncu: half of the issue slots of
+// the streamed kernel's pass 2 were address arithmetic).
+__device__ __forceinline__ unsigned lds_u32(unsigned a)
+{
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ unsigned lds_u16(unsigned a)
+{
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double lds_f64(unsigned a)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double2 lds_v2f64(unsigned a)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_v2f64(unsigned a, double x, double y)
+{
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) : "memory");
+}
 
 // DW = DMMA warps per CTA (8: one CTA per SM, 352 threads; 4: two CTAs per SM, 192 threads), NT = threads
 template <int NCT, int DW = 8, int NT = kThreads>
@@ -209,15 +249,23 @@ struct PackedEval {
                 mbar_wait(&full[0], 0);
             SQW_EPROF(1)
             const int ngw = (ngroups - warp + kDmmaWarps - 1) / kDmmaWarps;  // groups of this warp
+            // One shared address per lane and tile, immediate offsets for the warp's groups; the
+            // loads are unconditional (an absent group reads bytes of the next row or, past the last
+            // row, of the partial-logit buffer: multiplied by a zero V fragment) and the next tile's
+            // words are in flight while this tile's DMMAs issue.
+            const unsigned rows_s = smem_u32(rows) + (unsigned)(gid * rsq + 4 * qd + 16 * warp);
+            const unsigned plw = smem_u32(plog) + (unsigned)((((size_t)warp * cap8 + gid) * 8 + 2 * qd) * 8);
+            const unsigned tstride = (unsigned)(kTileRows * rsq);
+            unsigned cur[NBG], nxt[NBG];
+#pragma unroll
+            for (int i = 0; i < NBG; ++i)
+                cur[i] = nxt[i] = (ntiles > 0) ? lds_u32(rows_s + 16u * kDmmaWarps * i) : 0u;
 #pragma unroll 2
             for (int j = 0; j < ntiles; ++j) {
-                const unsigned char *rp = rows + (size_t)(kTileRows * j + gid) * rsq + 4 * qd;
-                unsigned wv[NBG];
+                const unsigned nb_ = rows_s + (unsigned)min(j + 1, ntiles - 1) * tstride;
 #pragma unroll
-                for (int i = 0; i < NBG; ++i) {
-                    const int g = warp + kDmmaWarps * i;
-                    wv[i] = (g < ngroups) ? *reinterpret_cast<const unsigned *>(rp + 16 * g) : 0u;
-                }
+                for (int i = 0; i < NBG; ++i)
+                    nxt[i] = lds_u32(nb_ + 16u * kDmmaWarps * i);
                 double pa[4][2];
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
@@ -226,15 +274,17 @@ struct PackedEval {
                 for (int i = 0; i < NBG; ++i) {
                     if (i >= NBG - 2 && i >= ngw)  // warp-uniform; an absent earlier group multiplies zeros
                         break;
-                    dmma884(pa[0], cvt_u8(wv[i] & 0xffu), wreg[4 * i + 0]);
-                    dmma884(pa[1], cvt_u8((wv[i] >> 8) & 0xffu), wreg[4 * i + 1]);
-                    dmma884(pa[2], cvt_u8((wv[i] >> 16) & 0xffu), wreg[4 * i + 2]);
-                    dmma884(pa[3], cvt_u8(wv[i] >> 24), wreg[4 * i + 3]);
+                    dmma884(pa[0], cvt_byte(cur[i], 0), wreg[4 * i + 0]);
+                    dmma884(pa[1], cvt_byte(cur[i], 1), wreg[4 * i + 1]);
+                    dmma884(pa[2], cvt_byte(cur[i], 2), wreg[4 * i + 2]);
+                    dmma884(pa[3], cvt_byte(cur[i], 3), wreg[4 * i + 3]);
                 }
                 // lane holds the partial S[row gid][class 2 qd + {0, 1}]
-                *reinterpret_cast<double2 *>(plog + ((size_t)warp * cap8 + kTileRows * j + gid) * 8 + 2 * qd) =
-                    make_double2((pa[0][0] + pa[1][0]) + (pa[2][0] + pa[3][0]),
-                                 (pa[0][1] + pa[1][1]) + (pa[2][1] + pa[3][1]));
+                sts_v2f64(plw + (unsigned)(kTileRows * 8 * 8) * j, (pa[0][0] + pa[1][0]) + (pa[2][0] + pa[3][0]),
+                          (pa[0][1] + pa[1][1]) + (pa[2][1] + pa[3][1]));
+#pragma unroll
+                for (int i = 0; i < NBG; ++i)
+                    cur[i] = nxt[i];
             }
         }
         loaded = true;
@@ -310,18 +360,28 @@ struct PackedEval {
                 for (int h = 0; h < 2; ++h)
                     acc[i][h][0] = acc[i][h][1] = 0.0;
             if (dmma_warp && hh * HG < ngw) {
+                const unsigned rs_ = smem_u32(rres) + (unsigned)((qd * 8 + gid) * 8);
+                const unsigned xs_ = smem_u32(rows) +
+                                     (unsigned)(qd * rsq + 2 * gid + 16 * warp + 16 * kDmmaWarps * hh * HG);
+                const unsigned half = (unsigned)(4 * rsq), tstride = (unsigned)(kTileRows * rsq);
+                double a0 = lds_f64(rs_), a1 = lds_f64(rs_ + 4 * 8 * 8), na0 = a0, na1 = a1;
+                unsigned x0[HG], x1[HG], nx0[HG], nx1[HG];
+#pragma unroll
+                for (int i = 0; i < HG; ++i) {
+                    x0[i] = nx0[i] = lds_u16(xs_ + 16u * kDmmaWarps * i);
+                    x1[i] = nx1[i] = lds_u16(xs_ + half + 16u * kDmmaWarps * i);
+                }
 #pragma unroll 2
                 for (int j = 0; j < ntiles; ++j) {
-                    const double a0 = rres[(size_t)(kTileRows * j + qd) * 8 + gid];      // R[row qd][class gid]
-                    const double a1 = rres[(size_t)(kTileRows * j + 4 + qd) * 8 + gid];  // R[row 4+qd][class gid]
-                    const unsigned char *rp0 = rows + (size_t)(kTileRows * j + qd) * rsq + 2 * gid;
-                    const unsigned char *rp1 = rp0 + 4 * (size_t)rsq;
-                    unsigned x0[HG], x1[HG];
+                    // operands of the next tile (clamped on the last) ahead of this tile's DMMAs
+                    const int jn = min(j + 1, ntiles - 1);
+                    const unsigned rn = rs_ + (unsigned)(kTileRows * 8 * 8) * jn, xn = xs_ + tstride * jn;
+                    na0 = lds_f64(rn);                  // R[row qd][class gid]
+                    na1 = lds_f64(rn + 4 * 8 * 8);      // R[row 4+qd][class gid]
 #pragma unroll
                     for (int i = 0; i < HG; ++i) {
-                        const int g = warp + kDmmaWarps * (hh * HG + i);
-                        x0[i] = (g < ngroups) ? *reinterpret_cast<const unsigned short *>(rp0 + 16 * g) : 0u;
-                        x1[i] = (g < ngroups) ? *reinterpret_cast<const unsigned short *>(rp1 + 16 * g) : 0u;
+                        nx0[i] = lds_u16(xn + 16u * kDmmaWarps * i);
+                        nx1[i] = lds_u16(xn + half + 16u * kDmmaWarps * i);
                     }
                     // rows 0..3 of every group first, then rows 4..7: an accumulator is re-used at a
                     // distance of 2 HG DMMAs (latency 26 cycles, issue 16)
@@ -329,15 +389,22 @@ struct PackedEval {
                     for (int i = 0; i < HG; ++i) {
                         if (hh * HG + i >= NBG - 2 && hh * HG + i >= ngw)  // warp-uniform
                             break;
-                        dmma884(acc[i][0], a0, cvt_u8(x0[i] & 0xffu));
-                        dmma884(acc[i][1], a0, cvt_u8(x0[i] >> 8));
+                        dmma884(acc[i][0], a0, cvt_byte(x0[i], 0));
+                        dmma884(acc[i][1], a0, cvt_byte(x0[i], 1));
                     }
 #pragma unroll
                     for (int i = 0; i < HG; ++i) {
                         if (hh * HG + i >= NBG - 2 && hh * HG + i >= ngw)
                             break;
-                        dmma884(acc[i][0], a1, cvt_u8(x1[i] & 0xffu));
-                        dmma884(acc[i][1], a1, cvt_u8(x1[i] >> 8));
+                        dmma884(acc[i][0], a1, cvt_byte(x1[i], 0));
+                        dmma884(acc[i][1], a1, cvt_byte(x1[i], 1));
+                    }
+                    a0 = na0;
+                    a1 = na1;
+#pragma unroll
+                    for (int i = 0; i < HG; ++i) {
+                        x0[i] = nx0[i];
+                        x1[i] = nx1[i];
                     }
                 }
             }

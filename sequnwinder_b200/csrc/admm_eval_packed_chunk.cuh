@@ -14,10 +14,17 @@
 //           stages of 32 rows x KC bytes fetched by the three helper warps with cp.async
 //           (16 B per lane, three stages deep), DMMA warps: one LDS.32 = 4 k-steps of one row,
 //           I2F.F64, DMMA for every class tile; partial logits of the 8 K-slices to shared memory,
-//           the helper warps add them into the global logits one stage behind;
+//           the helper warps add them into the global logits one stage behind (tree sum of the
+//           eight slices, RED.ADD.F64 into L2 from the second chunk on: no load to wait for);
 //   softmax one row per thread: logits - o -> residuals, NLL, class sums of the residuals;
 //   pass 2  per column chunk: G[:, chunk] += R^T n with the accumulators in registers, the
 //           residual rows of a stage staged next to its counts; mean / sd correction; one store.
+// Inner loops (ncu of the first version: DMMA pipe 50 % busy, half of pass 2's issue slots were
+// address arithmetic - every predicated LDS.U16 recomputed its generic address from %tid): all
+// shared-memory operands go through ONE 32-bit shared address per lane and stage plus immediate
+// offsets, the loads are unconditional (a stage row always holds KC bytes; absent groups are
+// skipped at the DMMAs), the four tiles of a stage are unrolled with the next tile's operands
+// loaded ahead of the current tile's DMMAs, and full chunks run a branch-free instantiation.
 #pragma once
 
 #include "admm_eval_packed.cuh"
@@ -34,10 +41,10 @@ struct PackedChunkCfg {
     static constexpr int KCS = KC + 16;                               // stage row stride in bytes (16 mod 128)
 };
 
-__device__ __forceinline__ void cp_async16(void *dst, const void *src, bool valid)
+__device__ __forceinline__ void cp_async16(unsigned dst_s, const void *src, bool valid)
 {
     const unsigned bytes = valid ? 16u : 0u;   // src-size 0: the 16 destination bytes are zero-filled
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_s), "l"(src), "r"(bytes)
                  : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
@@ -45,8 +52,9 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // Shared-memory carve-up (TileSmemLayout re-used): w = the solver's slice cache (one class tile
-// only), stage = kPcStages x (32 rows x KCS bytes | 32 x Cp residual doubles), plog = [2][8 warps]
-// [32 rows][Cp] partial logits, rs = 8 x Cp offset partials + Cp offsets + Cp class sums.
+// only), stage = kPcStages x (32 rows x KCS bytes | 32 x (Cp + 4) residual doubles: the row stride
+// Cp + 4 makes pass 2's fragment loads conflict-free), plog = [2][8 warps][32 rows][Cp] partial
+// logits, rs = 8 x Cp offset partials + Cp offsets + Cp class sums.
 inline TileSmemLayout packed_chunk_smem_layout(int Cp, size_t slice_bytes)
 {
     TileSmemLayout L{};
@@ -55,7 +63,7 @@ inline TileSmemLayout packed_chunk_smem_layout(int Cp, size_t slice_bytes)
     L.w_off = 0;
     L.w_bytes = (slice_bytes + 127) & ~(size_t)127;
     L.stage_off = L.w_bytes;
-    L.stage_bytes = (size_t)kPcRows * KCS + (size_t)kPcRows * Cp * sizeof(double);
+    L.stage_bytes = (size_t)kPcRows * KCS + (size_t)kPcRows * (Cp + 4) * sizeof(double);
     L.plog_off = L.stage_off + (size_t)kPcStages * L.stage_bytes;
     L.rs_off = L.plog_off + (size_t)2 * kDmmaWarps * kPcRows * Cp * sizeof(double);
     L.bar_off = L.rs_off + (size_t)(kDmmaWarps * Cp + 2 * Cp) * sizeof(double);
@@ -68,19 +76,23 @@ template <int NCT>
 struct PackedChunkEval {
     static constexpr int NBG = PackedChunkCfg<NCT>::NBG, KC = PackedChunkCfg<NCT>::KC,
                          KCS = PackedChunkCfg<NCT>::KCS, CP = NCT * 8;
+    static constexpr int RS = CP + 4;                          // residual row stride in a stage (doubles)
+    static constexpr int kHelpers = kThreads - kDmmaWarps * 32;  // 96 threads of the three helper warps
+    static constexpr int kTiles = kPcRows / 8;
+    static constexpr unsigned kPlogHalf = (unsigned)kDmmaWarps * kPcRows * CP * 8;  // bytes of one plog buffer
     const AdmmDev &P;
     int blk, cta, G;
-    unsigned char *stage0;
-    double *plog, *scr;
+    unsigned stage_s, plog_s;   // 32-bit shared addresses of stage 0 / the partial logits
+    double *scr;
     double *red;
-    size_t stage_bytes;
+    unsigned stage_bytes;
     int r0, r1, nst, nch, rsq;
 
     __device__ void init(unsigned char *smem, const TileSmemLayout &L, double *red_)
     {
-        stage0 = smem + L.stage_off;
-        stage_bytes = L.stage_bytes;
-        plog = reinterpret_cast<double *>(smem + L.plog_off);
+        stage_s = smem_u32(smem + L.stage_off);
+        stage_bytes = (unsigned)L.stage_bytes;
+        plog_s = smem_u32(smem + L.plog_off);
         scr = reinterpret_cast<double *>(smem + L.rs_off);
         red = red_;
         rsq = P.rsq;
@@ -92,40 +104,189 @@ struct PackedChunkEval {
     __device__ void set_profile(long long *) {}
     __device__ void drain() {}
 
-    __device__ __forceinline__ unsigned char *stage_rows(int s) const { return stage0 + (size_t)s * stage_bytes; }
-    __device__ __forceinline__ double *stage_res(int s) const
+    __device__ __forceinline__ unsigned stage_addr(int st) const
     {
-        return reinterpret_cast<double *>(stage0 + (size_t)s * stage_bytes + (size_t)kPcRows * KCS);
+        return stage_s + (unsigned)(st % kPcStages) * stage_bytes;
     }
 
     // helper warps: fetch stage `st` of column chunk `c` (and, in pass 2, its residual rows)
     __device__ void fetch(int c, int st, bool with_res, const double *Lb)
     {
         const int ht = (int)threadIdx.x - kDmmaWarps * 32;          // 0..95
-        const int nht = kThreads - kDmmaWarps * 32;
-        const int s = st % kPcStages;
+        const unsigned sb = stage_addr(st);
         const int wc = min(KC, P.dimp - c * KC);                      // bytes of this chunk (multiple of 16)
         const int pieces = wc >> 4;
         const int row0 = r0 + st * kPcRows;
-        unsigned char *dst = stage_rows(s);
         const unsigned char *src = P.Xq + ((size_t)blk * P.nb + row0) * rsq + (size_t)c * KC;
-        for (int i = ht; i < kPcRows * pieces; i += nht) {
-            const int r = i / pieces, q = i - r * pieces;
+        // copy i = ht + 96 k is piece q of row r: one division per call, then (r, q) advance by steps
+        int r = ht / pieces, q = ht - r * pieces;
+        const int dr = kHelpers / pieces, dq = kHelpers - dr * pieces;
+        while (r < kPcRows) {
             const bool valid = row0 + r < r1;
-            cp_async16(dst + (size_t)r * KCS + 16 * q, src + (valid ? (size_t)r * rsq + 16 * q : 0), valid);
+            cp_async16(sb + (unsigned)(r * KCS + 16 * q), src + (valid ? (size_t)r * rsq + 16 * q : 0), valid);
+            q += dq;
+            r += dr;
+            if (q >= pieces) {
+                q -= pieces;
+                ++r;
+            }
         }
         if (with_res) {
-            double *rd = stage_res(s);
-            const double *rsrc = Lb + (size_t)row0 * CP;
-            constexpr int per_row = CP * 8 / 16;
-            for (int i = ht; i < kPcRows * per_row; i += nht) {
-                const int r = i / per_row;
-                const bool valid = row0 + r < r1;
-                cp_async16(reinterpret_cast<unsigned char *>(rd) + 16 * i,
-                           reinterpret_cast<const unsigned char *>(rsrc) + (valid ? 16 * (size_t)i : 0), valid);
+            const unsigned rd = sb + (unsigned)(kPcRows * KCS);
+            const unsigned char *rsrc = reinterpret_cast<const unsigned char *>(Lb + (size_t)row0 * CP);
+            constexpr int per_row = CP / 2;   // 16-byte pieces of a residual row
+#pragma unroll
+            for (int k = 0; k < (kPcRows * per_row + kHelpers - 1) / kHelpers; ++k) {
+                const int i = ht + k * kHelpers;
+                if (i < kPcRows * per_row) {
+                    const int rr = i / per_row, qq = i - rr * per_row;
+                    const bool valid = row0 + rr < r1;
+                    cp_async16(rd + (unsigned)(rr * RS * 8 + 16 * qq), rsrc + (valid ? 16 * (size_t)i : 0), valid);
+                }
             }
         }
         cp_async_commit();
+    }
+
+    // helper warps: global logits of stage `st` (+)= tree sum of its 8 K-slices. First chunk: store;
+    // later chunks: RED.ADD.F64 into L2 (same thread, same address as the store: ordered).
+    __device__ __forceinline__ void accumulate(int c, int st, double *Lb) const
+    {
+        const int ht = (int)threadIdx.x - kDmmaWarps * 32;
+        const int row0 = r0 + st * kPcRows;
+        const unsigned pl = plog_s + (unsigned)(st & 1) * kPlogHalf;
+#pragma unroll
+        for (int k = 0; k < (kPcRows * CP / 2 + kHelpers - 1) / kHelpers; ++k) {
+            const int i = ht + k * kHelpers;
+            if (i < kPcRows * CP / 2) {
+                const int r = (2 * i) / CP, cc = 2 * i - r * CP;
+                if (row0 + r < r1) {
+                    double2 p[kDmmaWarps];
+#pragma unroll
+                    for (int w8 = 0; w8 < kDmmaWarps; ++w8)
+                        p[w8] = lds_v2f64(pl + (unsigned)(((w8 * kPcRows + r) * CP + cc) * 8));
+                    double2 v;
+                    v.x = ((p[0].x + p[1].x) + (p[2].x + p[3].x)) + ((p[4].x + p[5].x) + (p[6].x + p[7].x));
+                    v.y = ((p[0].y + p[1].y) + (p[2].y + p[3].y)) + ((p[4].y + p[5].y) + (p[6].y + p[7].y));
+                    double *lp = Lb + (size_t)(row0 + r) * CP + cc;
+                    if (c == 0) {
+                        __stcg(reinterpret_cast<double2 *>(lp), v);
+                    } else {
+                        atomicAdd(lp, v.x);
+                        atomicAdd(lp + 1, v.y);
+                    }
+                }
+            }
+        }
+    }
+
+    // DMMA warps, pass 1, one stage: partial logits of the four tiles over this warp's column groups.
+    // sb = stage + lane offset (row gid, byte 4 qd + 16 warp); pw = this warp's plog slice + lane offset.
+    template <bool FULL>
+    __device__ __forceinline__ void pass1_stage(unsigned sb, unsigned pw, const double (&vreg)[NBG * 4][NCT],
+                                                int ngw) const
+    {
+        unsigned cur[NBG], nxt[NBG];
+#pragma unroll
+        for (int i = 0; i < NBG; ++i)
+            cur[i] = nxt[i] = lds_u32(sb + 128u * i);
+#pragma unroll
+        for (int tt = 0; tt < kTiles; ++tt) {
+            if (tt + 1 < kTiles) {
+#pragma unroll
+                for (int i = 0; i < NBG; ++i)
+                    nxt[i] = lds_u32(sb + (unsigned)((tt + 1) * 8 * KCS) + 128u * i);
+            }
+            double pa[NCT][2][2];
+#pragma unroll
+            for (int ct = 0; ct < NCT; ++ct)
+                pa[ct][0][0] = pa[ct][0][1] = pa[ct][1][0] = pa[ct][1][1] = 0.0;
+#pragma unroll
+            for (int i = 0; i < NBG; ++i) {
+                if (!FULL && i >= ngw)  // warp-uniform
+                    break;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const double xa = cvt_byte(cur[i], t);
+#pragma unroll
+                    for (int ct = 0; ct < NCT; ++ct)
+                        dmma884(pa[ct][t & 1], xa, vreg[4 * i + t][ct]);
+                }
+            }
+            // lane holds the partial S[row gid][class ct*8 + 2 qd + {0, 1}]
+#pragma unroll
+            for (int ct = 0; ct < NCT; ++ct)
+                sts_v2f64(pw + (unsigned)((8 * tt * CP + ct * 8) * 8), pa[ct][0][0] + pa[ct][1][0],
+                          pa[ct][0][1] + pa[ct][1][1]);
+#pragma unroll
+            for (int i = 0; i < NBG; ++i)
+                cur[i] = nxt[i];
+        }
+    }
+
+    // DMMA warps, pass 2, one stage: acc += R^T n over the four tiles.
+    // sb = stage + lane offset (row qd, byte 2 gid + 16 warp); rb = residual rows + lane offset (row qd, class gid).
+    template <bool FULL>
+    __device__ __forceinline__ void pass2_stage(unsigned sb, unsigned rb, double (&acc)[NBG][2][NCT][2],
+                                                int ngw) const
+    {
+        double a0[NCT], a1[NCT], na0[NCT], na1[NCT];
+        unsigned x0[NBG], x1[NBG], nx0[NBG], nx1[NBG];
+#pragma unroll
+        for (int ct = 0; ct < NCT; ++ct) {
+            a0[ct] = na0[ct] = lds_f64(rb + (unsigned)(ct * 64));                  // R[row qd][class]
+            a1[ct] = na1[ct] = lds_f64(rb + (unsigned)((4 * RS + ct * 8) * 8));    // R[row 4+qd][class]
+        }
+#pragma unroll
+        for (int i = 0; i < NBG; ++i) {
+            x0[i] = nx0[i] = lds_u16(sb + 128u * i);
+            x1[i] = nx1[i] = lds_u16(sb + (unsigned)(4 * KCS) + 128u * i);
+        }
+#pragma unroll
+        for (int tt = 0; tt < kTiles; ++tt) {
+            if (tt + 1 < kTiles) {
+#pragma unroll
+                for (int ct = 0; ct < NCT; ++ct) {
+                    na0[ct] = lds_f64(rb + (unsigned)(((8 * tt + 8) * RS + ct * 8) * 8));
+                    na1[ct] = lds_f64(rb + (unsigned)(((8 * tt + 12) * RS + ct * 8) * 8));
+                }
+#pragma unroll
+                for (int i = 0; i < NBG; ++i) {
+                    nx0[i] = lds_u16(sb + (unsigned)((8 * tt + 8) * KCS) + 128u * i);
+                    nx1[i] = lds_u16(sb + (unsigned)((8 * tt + 12) * KCS) + 128u * i);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NBG; ++i) {
+                if (!FULL && i >= ngw)
+                    break;
+                const double b00 = cvt_byte(x0[i], 0), b01 = cvt_byte(x0[i], 1);
+                const double b10 = cvt_byte(x1[i], 0), b11 = cvt_byte(x1[i], 1);
+                // (an accumulator is re-used at a distance of 2 NCT DMMAs)
+#pragma unroll
+                for (int ct = 0; ct < NCT; ++ct)
+                    dmma884(acc[i][0][ct], a0[ct], b00);
+#pragma unroll
+                for (int ct = 0; ct < NCT; ++ct)
+                    dmma884(acc[i][1][ct], a0[ct], b01);
+#pragma unroll
+                for (int ct = 0; ct < NCT; ++ct)
+                    dmma884(acc[i][0][ct], a1[ct], b10);
+#pragma unroll
+                for (int ct = 0; ct < NCT; ++ct)
+                    dmma884(acc[i][1][ct], a1[ct], b11);
+            }
+#pragma unroll
+            for (int ct = 0; ct < NCT; ++ct) {
+                a0[ct] = na0[ct];
+                a1[ct] = na1[ct];
+            }
+#pragma unroll
+            for (int i = 0; i < NBG; ++i) {
+                x0[i] = nx0[i];
+                x1[i] = nx1[i];
+            }
+        }
     }
 
     __device__ double eval(const double *xcur)
@@ -138,6 +299,11 @@ struct PackedChunkEval {
         double *so = scr;                               // [8 warps][CP] offset partials
         double *o_all = scr + kDmmaWarps * CP;          // [CP] offsets o[c]
         double *sc_all = o_all + CP;                    // [CP] class sums of the residuals
+        // per-lane byte offsets into a stage / a plog slice (see pass1_stage / pass2_stage)
+        const unsigned off1 = (unsigned)(gid * KCS + 4 * qd + 16 * warp);
+        const unsigned off2 = (unsigned)(qd * KCS + 2 * gid + 16 * warp);
+        const unsigned offr = (unsigned)(kPcRows * KCS + (qd * RS + gid) * 8);
+        const unsigned offp = (unsigned)(((warp * kPcRows + gid) * CP + 2 * qd) * 8);
         if (dmma_warp && qd == 0)
             for (int ct = 0; ct < NCT; ++ct)
                 so[warp * CP + ct * 8 + gid] = 0.0;
@@ -146,6 +312,7 @@ struct PackedChunkEval {
         for (int c = 0; c < nch; ++c) {
             const int wc = min(KC, dimp - c * KC);
             const int ngroups = wc >> 4;
+            const int ngw = dmma_warp ? (ngroups - warp + kDmmaWarps - 1) / kDmmaWarps : 0;
             double vreg[NBG * 4][NCT];
             if (dmma_warp) {
                 // V fragments of this warp's column groups (constant for all tiles of the chunk)
@@ -157,18 +324,31 @@ struct PackedChunkEval {
                 for (int i = 0; i < NBG; ++i) {
                     const int g = warp + kDmmaWarps * i;
                     const int col = c * KC + 16 * g + 4 * qd;
+                    const bool ok = g < ngroups;
+                    double2 s01 = make_double2(0.0, 0.0), s23 = s01, m01 = s01, m23 = s01;
+                    if (ok) {
+                        s01 = __ldg(reinterpret_cast<const double2 *>(P.cinvsd + col));
+                        s23 = __ldg(reinterpret_cast<const double2 *>(P.cinvsd + col + 2));
+                        m01 = __ldg(reinterpret_cast<const double2 *>(P.cmean + col));
+                        m23 = __ldg(reinterpret_cast<const double2 *>(P.cmean + col + 2));
+                    }
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const bool ok = g < ngroups;
-                        const double is = ok ? __ldg(P.cinvsd + col + t) : 0.0;
-                        const double mu = ok ? __ldg(P.cmean + col + t) : 0.0;
-#pragma unroll
-                        for (int ct = 0; ct < NCT; ++ct) {
-                            const int cls = ct * 8 + gid;
-                            const double w = (ok && cls < P.C) ? __ldcg(xcur + (size_t)cls * dimp + col + t) : 0.0;
-                            vreg[4 * i + t][ct] = w * is;
-                            pb[ct] += mu * vreg[4 * i + t][ct];
+                    for (int ct = 0; ct < NCT; ++ct) {
+                        const int cls = ct * 8 + gid;
+                        double2 w01 = make_double2(0.0, 0.0), w23 = w01;
+                        if (ok && cls < P.C) {
+                            const double *wg = xcur + (size_t)cls * dimp + col;
+                            w01 = __ldcg(reinterpret_cast<const double2 *>(wg));
+                            w23 = __ldcg(reinterpret_cast<const double2 *>(wg + 2));
                         }
+                        vreg[4 * i + 0][ct] = w01.x * s01.x;
+                        vreg[4 * i + 1][ct] = w01.y * s01.y;
+                        vreg[4 * i + 2][ct] = w23.x * s23.x;
+                        vreg[4 * i + 3][ct] = w23.y * s23.y;
+                        pb[ct] += m01.x * vreg[4 * i + 0][ct];
+                        pb[ct] += m01.y * vreg[4 * i + 1][ct];
+                        pb[ct] += m23.x * vreg[4 * i + 2][ct];
+                        pb[ct] += m23.y * vreg[4 * i + 3][ct];
                     }
                 }
 #pragma unroll
@@ -189,41 +369,16 @@ struct PackedChunkEval {
                 cp_async_wait<1>();
             }
             __syncthreads();
-            const int ngw = dmma_warp ? (ngroups - warp + kDmmaWarps - 1) / kDmmaWarps : 0;
+            const bool full = ngw == NBG;
             for (int st = 0; st <= nst; ++st) {
                 if (dmma_warp) {
                     if (st < nst) {
-                        const unsigned char *rows = stage_rows(st % kPcStages);
-                        double *pl = plog + ((size_t)(st & 1) * kDmmaWarps + warp) * kPcRows * CP;
-#pragma unroll 1
-                        for (int tt = 0; tt < kPcRows / 8; ++tt) {
-                            const unsigned char *rp = rows + (size_t)(8 * tt + gid) * KCS + 4 * qd;
-                            unsigned wv[NBG];
-#pragma unroll
-                            for (int i = 0; i < NBG; ++i)
-                                wv[i] = (i < ngw) ? *reinterpret_cast<const unsigned *>(rp + 16 * (warp + kDmmaWarps * i)) : 0u;
-                            double pa[NCT][2][2];
-#pragma unroll
-                            for (int ct = 0; ct < NCT; ++ct)
-                                pa[ct][0][0] = pa[ct][0][1] = pa[ct][1][0] = pa[ct][1][1] = 0.0;
-#pragma unroll
-                            for (int i = 0; i < NBG; ++i) {
-                                if (i >= ngw)  // warp-uniform
-                                    break;
-#pragma unroll
-                                for (int t = 0; t < 4; ++t) {
-                                    const double xa = cvt_u8((wv[i] >> (8 * t)) & 0xffu);
-#pragma unroll
-                                    for (int ct = 0; ct < NCT; ++ct)
-                                        dmma884(pa[ct][t & 1], xa, vreg[4 * i + t][ct]);
-                                }
-                            }
-                            // lane holds the partial S[row gid][class ct*8 + 2 qd + {0, 1}]
-#pragma unroll
-                            for (int ct = 0; ct < NCT; ++ct)
-                                *reinterpret_cast<double2 *>(pl + (size_t)(8 * tt + gid) * CP + ct * 8 + 2 * qd) =
-                                    make_double2(pa[ct][0][0] + pa[ct][1][0], pa[ct][0][1] + pa[ct][1][1]);
-                        }
+                        const unsigned sb = stage_addr(st) + off1;
+                        const unsigned pw = plog_s + (unsigned)(st & 1) * kPlogHalf + offp;
+                        if (full)
+                            pass1_stage<true>(sb, pw, vreg, ngw);
+                        else
+                            pass1_stage<false>(sb, pw, vreg, ngw);
                     }
                 } else {
                     // helper warps: next fetch, then the logits of the PREVIOUS stage += its 8 K-slices
@@ -231,31 +386,8 @@ struct PackedChunkEval {
                         fetch(c, st + 2, false, Lb);
                     else
                         cp_async_commit();
-                    if (st >= 1) {
-                        const int ht = (int)threadIdx.x - kDmmaWarps * 32;
-                        const int row0 = r0 + (st - 1) * kPcRows;
-                        const double *pl = plog + (size_t)((st - 1) & 1) * kDmmaWarps * kPcRows * CP;
-                        for (int i = ht; i < kPcRows * CP / 2; i += kThreads - kDmmaWarps * 32) {
-                            const int r = (2 * i) / CP, cc = 2 * i - r * CP;
-                            if (row0 + r < r1) {
-                                double2 v = *reinterpret_cast<const double2 *>(pl + (size_t)r * CP + cc);
-#pragma unroll
-                                for (int w8 = 1; w8 < kDmmaWarps; ++w8) {
-                                    const double2 pv = *reinterpret_cast<const double2 *>(
-                                        pl + ((size_t)w8 * kPcRows + r) * CP + cc);
-                                    v.x += pv.x;
-                                    v.y += pv.y;
-                                }
-                                double2 *lp = reinterpret_cast<double2 *>(Lb + (size_t)(row0 + r) * CP + cc);
-                                if (c > 0) {
-                                    const double2 old = *lp;
-                                    v.x += old.x;
-                                    v.y += old.y;
-                                }
-                                *lp = v;
-                            }
-                        }
-                    }
+                    if (st >= 1)
+                        accumulate(c, st - 1, Lb);
                     cp_async_wait<1>();
                 }
                 __syncthreads();
@@ -271,6 +403,7 @@ struct PackedChunkEval {
         __syncthreads();
 
         // ---------------- softmax over my rows: logits -> residuals, NLL, class sums ----------------
+        // (the logits were accumulated in L2 by RED: read them past L1)
         double facc = 0.0;
         double rsum[CP];
 #pragma unroll
@@ -284,30 +417,41 @@ struct PackedChunkEval {
                 double lv[CP];
                 double mx = -INFINITY;
 #pragma unroll
-                for (int cc = 0; cc < CP; ++cc) {
-                    lv[cc] = lp[cc] - o_all[cc];
+                for (int cc = 0; cc < CP; cc += 2) {
+                    const double2 l2 = __ldcg(reinterpret_cast<const double2 *>(lp + cc));
+                    lv[cc] = l2.x - o_all[cc];
+                    lv[cc + 1] = l2.y - o_all[cc + 1];
+                }
+#pragma unroll
+                for (int cc = 0; cc < CP; ++cc)
                     if (cc < P.C)
                         mx = fmax(mx, lv[cc]);
-                }
+                const int cls = yb[row];
+                const double wi = wb[row];
+                const double lcls = __ldcg(lp + cls) - o_all[cls];
                 double den = 0.0;
 #pragma unroll
                 for (int cc = 0; cc < CP; ++cc) {
                     lv[cc] = (cc < P.C) ? exp(lv[cc] - mx) : 0.0;
                     den += lv[cc];
                 }
-                const int cls = yb[row];
-                const double wi = wb[row];
-                facc -= wi * ((lp[cls] - o_all[cls] - mx) - log(den));
+                facc -= wi * ((lcls - mx) - log(den));
 #pragma unroll
-                for (int cc = 0; cc < CP; ++cc) {
-                    double r = 0.0;
+                for (int cc = 0; cc < CP; cc += 2) {
+                    double ra = 0.0, rb = 0.0;
                     if (cc < P.C) {
-                        r = wi * (lv[cc] / den);
+                        ra = wi * (lv[cc] / den);
                         if (cc == cls)
-                            r -= wi;
+                            ra -= wi;
                     }
-                    lp[cc] = r;
-                    rsum[cc] += r;
+                    if (cc + 1 < P.C) {
+                        rb = wi * (lv[cc + 1] / den);
+                        if (cc + 1 == cls)
+                            rb -= wi;
+                    }
+                    *reinterpret_cast<double2 *>(lp + cc) = make_double2(ra, rb);
+                    rsum[cc] += ra;
+                    rsum[cc + 1] += rb;
                 }
             }
         }
@@ -343,48 +487,14 @@ struct PackedChunkEval {
                 cp_async_wait<1>();
             }
             __syncthreads();
+            const bool full = ngw == NBG;
             for (int st = 0; st < nst; ++st) {
                 if (dmma_warp) {
-                    const unsigned char *rows = stage_rows(st % kPcStages);
-                    const double *res = stage_res(st % kPcStages);
-#pragma unroll 1
-                    for (int tt = 0; tt < kPcRows / 8; ++tt) {
-                        double a0[NCT], a1[NCT];
-#pragma unroll
-                        for (int ct = 0; ct < NCT; ++ct) {
-                            a0[ct] = res[(size_t)(8 * tt + qd) * CP + ct * 8 + gid];       // R[row qd][class]
-                            a1[ct] = res[(size_t)(8 * tt + 4 + qd) * CP + ct * 8 + gid];   // R[row 4+qd][class]
-                        }
-                        const unsigned char *rp0 = rows + (size_t)(8 * tt + qd) * KCS + 2 * gid;
-                        const unsigned char *rp1 = rp0 + 4 * (size_t)KCS;
-                        unsigned x0[NBG], x1[NBG];
-#pragma unroll
-                        for (int i = 0; i < NBG; ++i) {
-                            const int off = 16 * (warp + kDmmaWarps * i);
-                            x0[i] = (i < ngw) ? *reinterpret_cast<const unsigned short *>(rp0 + off) : 0u;
-                            x1[i] = (i < ngw) ? *reinterpret_cast<const unsigned short *>(rp1 + off) : 0u;
-                        }
-#pragma unroll
-                        for (int i = 0; i < NBG; ++i) {
-                            if (i >= ngw)
-                                break;
-                            const double b00 = cvt_u8(x0[i] & 0xffu), b01 = cvt_u8(x0[i] >> 8);
-                            const double b10 = cvt_u8(x1[i] & 0xffu), b11 = cvt_u8(x1[i] >> 8);
-                            // (an accumulator is re-used at a distance of 2 NCT DMMAs)
-#pragma unroll
-                            for (int ct = 0; ct < NCT; ++ct)
-                                dmma884(acc[i][0][ct], a0[ct], b00);
-#pragma unroll
-                            for (int ct = 0; ct < NCT; ++ct)
-                                dmma884(acc[i][1][ct], a0[ct], b01);
-#pragma unroll
-                            for (int ct = 0; ct < NCT; ++ct)
-                                dmma884(acc[i][0][ct], a1[ct], b10);
-#pragma unroll
-                            for (int ct = 0; ct < NCT; ++ct)
-                                dmma884(acc[i][1][ct], a1[ct], b11);
-                        }
-                    }
+                    const unsigned sa = stage_addr(st);
+                    if (full)
+                        pass2_stage<true>(sa + off2, sa + offr, acc, ngw);
+                    else
+                        pass2_stage<false>(sa + off2, sa + offr, acc, ngw);
                 } else {
                     if (st + 2 < nst)
                         fetch(c, st + 2, true, Lb);
