@@ -582,9 +582,14 @@ def run_cfg2(args, info, world, dev, comm, dist, torch):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the caller's count matrix is allocated once and re-used by every step, as the Java side keeps
+    # its int[n][numK]: a fresh 102 MB array per call costs 2 ms of first-touch page faults
+    # (gpurun_out/r2_kmerhost24.log: 3.6 against 1.6 ms per call)
+    host_counts = np.empty((my_offs.size - 1, kc.numK), dtype=np.int32)
+
     def e2e_step():
         t0 = time.time()
-        cnt, hn = kc.count(my_bases, my_offs)
+        cnt, hn = kc.count(my_bases, my_offs, out=host_counts)
         t1 = time.time()
         lo2 = job.optimizer(None, None)
         lo2._open()          # handle + problem upload (execute() would do it)
@@ -849,6 +854,14 @@ def run_big(args, info, world, dev, comm, dist, torch):
     peak, peak_src = measured_peak_hbm()
     achieved = eval_bytes_all / world / eval_s / 1e9
     value = nb * T * iters / admm_s
+    # fp64 tensor (DMMA) roofline of the packed-count kernels: useful FLOPs 4 n_b C dim per block
+    # evaluation (two products, LOne.java:936-1049) against the DMMA peak this repo measured on B200
+    # (profiles/r01_microbench_dmma.log: 36.6 TFLOP/s at 16 cycles per m8n8k4 and sub-partition;
+    # MEASURED_PEAKS.json only holds the bf16 figure, which no fp64 path can use)
+    dmma_peak = 36.6
+    flops_useful = 4.0 * nb * C * dim * evals_all / world
+    Cp = (C + 7) // 8 * 8
+    flops_issued = 4.0 * nb * Cp * ((dim + 15) // 16 * 16) * evals_all / world
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_s / args.steps * 1e3, "higher_is_better": True,
@@ -856,8 +869,11 @@ def run_big(args, info, world, dev, comm, dist, torch):
         "config": {"workload": workload_string(cfg, world, "strong", A), "sites": sites, "admm_blocks": T,
                    "rows_per_block": nb, "blocks_per_gpu": T // world, "columns": dim, "classes": C,
                    "eval_mode": mode,
-                   "l2": "the training matrix of a rank (GBs) is far larger than L2 (126 MB): every "
-                         "evaluation streams it from HBM",
+                   "representation": ("packed k-mer counts (uint8) + xMean / xSD, streamed column chunk by "
+                                      "column chunk (csrc/admm_eval_packed_chunk.cuh)" if mode == 10 else
+                                      "fp64 standardised matrix"),
+                   "l2": "the training matrix of a rank (GBs as bytes, 8x that as fp64) is far larger than L2 "
+                         "(126 MB): every evaluation streams it from HBM twice",
                    "step": f"{A} ADMM iterations of outer iteration 1 on the resident matrix"},
         "parity": {"ranks_bitwise_equal": same, "finite": bool(np.isfinite(x_fin).all()),
                    "oracle": "reduced-size shapes of this configuration in tests/ (-m gpu); the oracle "
@@ -875,8 +891,18 @@ def run_big(args, info, world, dev, comm, dist, torch):
         "roofline": {"bound": "hbm", "kernel": "admm_xupdate_kernel", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": eval_bytes_all / world / max(1, iters),
-                     "note": "per GPU: two-pass algorithmic bytes of the rank's evaluations over the "
-                             "summed durations of its x-update launches (max over ranks)"},
+                     "note": "per GPU: two-pass fp64 algorithmic bytes (SURVEY 8d) of the rank's evaluations over "
+                             "the summed durations of its x-update launches (max over ranks). The packed-count "
+                             "kernels move 1/8 of these bytes; what bounds them is roofline_fp64_tensor"},
+        "roofline_fp64_tensor": {"bound": "tensor", "kernel": "admm_xupdate_kernel", "unit": "TFLOP/s",
+                                 "achieved": flops_useful / eval_s / 1e12, "peak": dmma_peak,
+                                 "frac": flops_useful / eval_s / 1e12 / dmma_peak,
+                                 "issued": flops_issued / eval_s / 1e12,
+                                 "frac_issued": flops_issued / eval_s / 1e12 / dmma_peak,
+                                 "peak_source": "profiles/r01_microbench_dmma.log (DMMA m8n8k4, this pool's B200)",
+                                 "note": "achieved = 4 n_b C dim FLOPs per block evaluation; issued also counts "
+                                         "the classes padded to a multiple of 8 (C = 12 -> 16, 17 -> 24) and "
+                                         "columns padded to 16, which the DMMA tiles execute"},
         "e2e": {"value": nb * T * iters / (admm_s + (kmer_s + plan_s + build_s) * args.steps), "unit": UNIT,
                 "h2d_bytes_per_step": int(d_bases.numel() * world + 12 * sites),
                 "d2h_bytes_per_step": int(2 * (x0.nbytes + smx0.nbytes)),
