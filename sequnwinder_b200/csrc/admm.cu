@@ -153,8 +153,12 @@ struct sqw_admm {
     template <typename Tp>
     int dalloc(Tp **p, size_t count, bool zero = true)
     {
+        // stream-ordered allocation from the device's default pool (its release threshold is raised
+        // in sqw_admm_create): a handle's ~50 buffers come out of memory the previous handle gave
+        // back, where cudaMalloc / cudaFree cost the e2e step 0.1 s per training (each cudaFree
+        // synchronises the device)
         const size_t bytes = std::max<size_t>(count, 1) * sizeof(Tp);
-        SQW_CUDA_CHECK(cudaMalloc((void **)p, bytes));
+        SQW_CUDA_CHECK(cudaMallocAsync((void **)p, bytes, stream));
         allocs.push_back((void *)*p);
         if (zero)
             SQW_CUDA_CHECK(cudaMemsetAsync(*p, 0, bytes, stream));
@@ -535,6 +539,14 @@ int sqw_admm_create(sqw_admm **out)
     sqw_admm *h = new sqw_admm();
     SQW_CUDA_CHECK(cudaGetDevice(&h->device));
     SQW_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    {   // keep what destroyed handles free in the device's default pool (dalloc): by default a pool
+        // hands everything back to the driver at the next synchronisation
+        cudaMemPool_t pool = nullptr;
+        unsigned long long keep = ~0ull;
+        if (cudaDeviceGetDefaultMemPool(&pool, h->device) != cudaSuccess ||
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) != cudaSuccess)
+            cudaGetLastError();   // older drivers: the allocations still work, only slower
+    }
     if (const char *env = getenv("SQW_ADMM_CAPS")) {  // tuning hook (header): comma separated caps
         int i = 0;
         for (const char *q = env; *q && i < kNumPhases - 1; ++i) {
@@ -562,7 +574,9 @@ void sqw_admm_destroy(sqw_admm *h)
     }
     // the NCCL communicator is shared between handles and outlives them (see sqw_admm_set_comm)
     for (void *p : h->allocs)
-        cudaFree(p);
+        cudaFreeAsync(p, h->stream);
+    if (h->stream)
+        cudaStreamSynchronize(h->stream);
     if (h->h_ring) {
         cudaFreeHost(h->h_ring);
         for (int i = 0; i < kRing; ++i) {
@@ -1084,11 +1098,11 @@ int sqw_admm_set_problem_counts(sqw_admm *h, int64_t n_rows, int32_t dim, int32_
     uint8_t *d_src = nullptr;
     double *d_ms = nullptr, *d_w = nullptr;
     int *d_y = nullptr;
-    cudaError_t e = cudaMalloc((void **)&d_src, (size_t)n_rows * F);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_ms, sizeof(double) * 2 * dim);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_w, sizeof(double) * n_rows);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_y, sizeof(int) * n_rows);
     cudaStream_t st = h->stream;
+    cudaError_t e = cudaMallocAsync((void **)&d_src, (size_t)n_rows * F, st);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_ms, sizeof(double) * 2 * dim, st);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_w, sizeof(double) * n_rows, st);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_y, sizeof(int) * n_rows, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_src, counts, (size_t)n_rows * F, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_ms, mean, sizeof(double) * dim, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_ms + dim, sd, sizeof(double) * dim, cudaMemcpyHostToDevice, st);
@@ -1097,10 +1111,12 @@ int sqw_admm_set_problem_counts(sqw_admm *h, int64_t n_rows, int32_t dim, int32_
     rc = (e == cudaSuccess) ? build_from_counts<uint8_t>(h, d_src, (long long)F, nullptr, d_ms, d_ms + dim,
                                                           d_y, d_w, 0, st)
                             : set_error(SQW_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e));
-    cudaFree(d_src);
-    cudaFree(d_ms);
-    cudaFree(d_w);
-    cudaFree(d_y);
+    // (the host buffers are pageable: every copy above has returned from the host's side, and the
+    // frees are ordered behind the gather on the stream)
+    if (d_src) cudaFreeAsync(d_src, st);
+    if (d_ms) cudaFreeAsync(d_ms, st);
+    if (d_w) cudaFreeAsync(d_w, st);
+    if (d_y) cudaFreeAsync(d_y, st);
     return rc;
 }
 
