@@ -36,7 +36,9 @@ extern "C" {
 /* Environment hooks read by the library (none is needed in production; defaults in brackets):
  *   tests      SQW_ADMM_EVAL_MODE=1|2|6   force a more general fp64 evaluation path
  *              SQW_ADMM_NO_PACKED=1       count matrices always through the fp64 kernels
- *              SQW_ADMM_PACKED_MODE=9     packed counts with two CTAs per SM (built, measured slower)
+ *              SQW_ADMM_PACKED_MODE=9|10  packed counts with two CTAs per SM (built, measured slower) /
+ *                                         always through the streamed packed kernels (what long rows,
+ *                                         more than 8 classes and budgeted handles use anyway)
  *              SQW_ADMM_UNFUSED=1         iteration tail as separate kernels / two collectives
  *   profiling  SQW_ADMM_PROFILE=1         per-phase timers of the x-update kernel on stderr
  *              SQW_ADMM_TAIL_PROFILE=1    multi-GPU: events between the kernels of the iteration tail
@@ -134,10 +136,12 @@ int sqw_admm_set_problem_dev(sqw_admm *h, int64_t n_rows, int32_t dim, int32_t n
  * rows_local = 1 (multi-GPU, sqw_admm_set_comm): they hold only the rows of this rank's blocks,
  * i.e. the rows i < floor(n_rows / T) * T with (i mod T) mod world == rank in ascending order of i,
  * so that every rank featurises its own sequences only (mean / sd stay the statistics of ALL rows).
- * Shapes the packed kernels do not cover (more than 8 classes, rows longer than 768 columns, a
- * block too large for shared memory) are expanded to the fp64 matrix on the device and run through
- * the fp64 kernels: the call always succeeds for valid counts. Counts above 255 ->
- * SQW_ERR_UNSUPPORTED. Synchronises `stream`. */
+ * Two packed kernels cover every shape: where a CTA's rows of its block fit shared memory (up to 8
+ * classes, rows up to 768 columns: BASELINE configs[0..1]) they stay there for the whole launch;
+ * otherwise (longer rows, up to 24 classes, blocks of any size: configs[2..3], and handles with a
+ * CTA budget) they are streamed as byte tiles, column chunk by column chunk. The
+ * call always succeeds for valid counts. Counts above 255 -> SQW_ERR_UNSUPPORTED. Synchronises
+ * `stream`. */
 int sqw_admm_set_problem_counts(sqw_admm *h, int64_t n_rows, int32_t dim, int32_t num_classes,
                                 const uint8_t *counts, const double *mean, const double *sd,
                                 const int32_t *y, const double *w);
