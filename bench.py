@@ -873,7 +873,9 @@ def run_big(args, info, world, dev, comm, dist, torch):
     # MEASURED_PEAKS.json only holds the bf16 figure, which no fp64 path can use)
     dmma_peak = 36.6
     flops_useful = 4.0 * nb * C * dim * evals_all / world
-    Cp = (C + 7) // 8 * 8
+    # classes the fp64 pipe works on: padded to whole 8-class DMMA tiles, except for C = 8 n + 1 in
+    # mode 11 (n tiles + the last class as DFMAs)
+    Cp = C if mode == 11 else (C + 7) // 8 * 8
     flops_issued = 4.0 * nb * Cp * ((dim + 15) // 16 * 16) * evals_all / world
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -883,7 +885,7 @@ def run_big(args, info, world, dev, comm, dist, torch):
                    "rows_per_block": nb, "blocks_per_gpu": T // world, "columns": dim, "classes": C,
                    "eval_mode": mode,
                    "representation": ("packed k-mer counts (uint8) + xMean / xSD, streamed column chunk by "
-                                      "column chunk (csrc/admm_eval_packed_chunk.cuh)" if mode == 10 else
+                                      "column chunk (csrc/admm_eval_packed_chunk.cuh)" if mode in (10, 11) else
                                       "fp64 standardised matrix"),
                    "l2": "the training matrix of a rank (GBs as bytes, 8x that as fp64) is far larger than L2 "
                          "(126 MB): every evaluation streams it from HBM twice",
@@ -914,8 +916,9 @@ def run_big(args, info, world, dev, comm, dist, torch):
                                  "frac_issued": flops_issued / eval_s / 1e12 / dmma_peak,
                                  "peak_source": "profiles/r01_microbench_dmma.log (DMMA m8n8k4, this pool's B200)",
                                  "note": "achieved = 4 n_b C dim FLOPs per block evaluation; issued also counts "
-                                         "the classes padded to a multiple of 8 (C = 12 -> 16, 17 -> 24) and "
-                                         "columns padded to 16, which the DMMA tiles execute"},
+                                         "the classes padded to a multiple of 8 (C = 12 -> 16; C = 17 runs as "
+                                         "16 + 1 in mode 11, 24 in mode 10) and columns padded to 16, which "
+                                         "the fp64 pipe executes"},
         "e2e": {"value": nb * T * iters / (admm_s + (kmer_s + plan_s + build_s) * args.steps), "unit": UNIT,
                 "h2d_bytes_per_step": int(d_bases.numel() * world + 12 * sites),
                 "d2h_bytes_per_step": int(2 * (x0.nbytes + smx0.nbytes)),

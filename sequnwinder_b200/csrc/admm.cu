@@ -182,6 +182,8 @@ static XKernel xupdate_kernel(int nct, int mode)
     case 16 + 10: return admm_xupdate_kernel<1, 10>;
     case 32 + 10: return admm_xupdate_kernel<2, 10>;
     case 48 + 10: return admm_xupdate_kernel<3, 10>;
+    case 16 + 11: return admm_xupdate_kernel<1, 11>;
+    case 32 + 11: return admm_xupdate_kernel<2, 11>;
     case 16 + 1: return admm_xupdate_kernel<1, 1>;
     case 16 + 2: return admm_xupdate_kernel<1, 2>;
     case 32 + 4: return admm_xupdate_kernel<2, 4>;
@@ -207,6 +209,8 @@ static EKernel eval_kernel(int nct, int mode)
     case 16 + 10: return admm_eval_kernel<1, 10>;
     case 32 + 10: return admm_eval_kernel<2, 10>;
     case 48 + 10: return admm_eval_kernel<3, 10>;
+    case 16 + 11: return admm_eval_kernel<1, 11>;
+    case 32 + 11: return admm_eval_kernel<2, 11>;
     case 16 + 1: return admm_eval_kernel<1, 1>;
     case 16 + 2: return admm_eval_kernel<1, 2>;
     case 32 + 4: return admm_eval_kernel<2, 4>;
@@ -221,6 +225,8 @@ static EKernel eval_kernel(int nct, int mode)
     return nullptr;
 }
 
+// class tiles of the kernel instantiation: MODE 11 runs C = 8 n + 1 classes on n DMMA class tiles
+static int kernel_nct(const sqw_admm *h) { return h->eval_mode == 11 ? (h->C - 1) / 8 : h->dev.Cp / 8; }
 static int mode_threads(int mode) { return mode == 9 ? ModeCfg<9>::NT : kThreads; }
 static int mode_ctas_per_sm(int mode) { return mode == 9 ? ModeCfg<9>::MINB : 1; }
 
@@ -283,7 +289,7 @@ static int prepare(sqw_admm *h)
     D.n_sm = 148;
     // MODE 9 probe: start delay of the second CTA of every SM (measured: no effect, see plan_blocks)
     D.skew_ns = getenv("SQW_ADMM_SKEW_NS") ? atoi(getenv("SQW_ADMM_SKEW_NS")) : 0;
-    const int nct = D.Cp / 8;
+    const int nct = kernel_nct(h);
     if ((long long)D.Cp * D.dimp * h->dev.T_local > (1ll << 31) - 1 || (long long)D.upad > (1 << 30))
         return set_error(SQW_ERR_UNSUPPORTED, "problem too large for 32-bit coordinate indices");
 
@@ -295,7 +301,7 @@ static int prepare(sqw_admm *h)
         n_sm = std::min(n_sm, h->cta_budget);
     const int mode = h->eval_mode;
     const size_t w_bytes = (size_t)D.Cp * D.wstride * sizeof(double);
-    if (mode == 4 || mode == 5 || mode == 6 || mode == 8 || mode == 9 || mode == 10)
+    if (mode == 4 || mode == 5 || mode == 6 || mode == 8 || mode == 9 || mode == 10 || mode == 11)
         h->xupdate_smem = h->layout.total;
     else if (mode == 1)
         h->xupdate_smem = w_bytes;
@@ -441,7 +447,7 @@ static int prepare(sqw_admm *h)
 static int launch_xupdate(sqw_admm *h)
 {
     AdmmDev &D = h->dev;
-    XKernel xk = xupdate_kernel(D.Cp / 8, h->eval_mode);
+    XKernel xk = xupdate_kernel(kernel_nct(h), h->eval_mode);
     for (int ph = 0; ph < h->nphase; ++ph) {
         int phase = ph, cap = (ph == h->nphase - 1) ? 0x7fffffff : h->caps[ph];
         void *args[] = {&D, &h->layout, &phase, &cap};
@@ -866,12 +872,25 @@ static int plan_blocks(sqw_admm *h, int64_t n_rows, int32_t dim, int32_t num_cla
         // any shape: the streamed, column-chunked packed evaluation (admm_eval_packed_chunk.cuh);
         // replaced below by the resident one where the rows fit shared memory
         const int dimp16 = (dim + 15) / 16 * 16;
-        TileSmemLayout Lq = packed_chunk_smem_layout(Cp, nct == 1 ? kSolveSliceBytes : 0);
+        TileSmemLayout Lq = packed_chunk_smem_layout(nct, false, nct == 1 ? kSolveSliceBytes : 0);
         if (Lq.total <= budget) {
             h->eval_mode = 10;
             h->layout = Lq;
             D.dimp = dimp16;
             D.rsq = dimp16;
+        }
+        // C = 9 or 17 (2^k labels + one outgroup class): one class tile less, the last class as
+        // DFMAs next to the DMMAs (MODE 11). SQW_ADMM_PACKED_MODE=10 keeps the padded form.
+        const char *force = getenv("SQW_ADMM_PACKED_MODE");
+        if ((num_classes == 9 || num_classes == 17) && !(force && atoi(force) == 10)) {
+            const int nx = (num_classes - 1) / 8;
+            TileSmemLayout Lx = packed_chunk_smem_layout(nx, true, nx == 1 ? kSolveSliceBytes : 0);
+            if (Lx.total <= budget) {
+                h->eval_mode = 11;
+                h->layout = Lx;
+                D.dimp = dimp16;
+                D.rsq = dimp16;
+            }
         }
     }
     if (packed_ok && nct == 1 && dim <= kPackedMaxDim && !(getenv("SQW_ADMM_PACKED_MODE") &&
@@ -1047,7 +1066,7 @@ static int build_from_counts(sqw_admm *h, const SrcT *d_src, long long src_strid
     admm_packed_stats_kernel<<<(D.dimp + 255) / 256, 256, 0, st>>>(d_mean, d_sd, d_col_idx, D.dim, D.dimp,
                                                                    mean_p, invsd_p, mean_f, sd_f);
     const int grid = (int)std::min<size_t>(rows, 148 * 16);
-    if (h->eval_mode == 8 || h->eval_mode == 9 || h->eval_mode == 10) {
+    if (h->eval_mode == 8 || h->eval_mode == 9 || h->eval_mode == 10 || h->eval_mode == 11) {
         unsigned char *dXq = nullptr;
         if ((rc = h->dalloc(&dXq, rows * D.rsq + 16384, false)) != SQW_OK) return rc;
         admm_gather_counts_kernel<SrcT, true><<<grid, 256, 0, st>>>(
@@ -1442,7 +1461,7 @@ int sqw_admm_eval(sqw_admm *h, const double *cx, const double *smx, double pho, 
     double *d_f = nullptr;
     SQW_CUDA_CHECK(cudaMalloc((void **)&d_f, sizeof(double) * D.T_local));
     SQW_CUDA_CHECK(cudaMemsetAsync(d_f, 0, sizeof(double) * D.T_local, st));
-    EKernel ek = eval_kernel(D.Cp / 8, h->eval_mode);
+    EKernel ek = eval_kernel(kernel_nct(h), h->eval_mode);
     void *args[] = {&D, &h->layout, &pho, &d_f};
     cudaError_t e = cudaLaunchCooperativeKernel((void *)ek, dim3(D.Gmax), dim3(mode_threads(h->eval_mode)),
                                                 args, h->xupdate_smem, st);

@@ -25,6 +25,15 @@
 // offsets, the loads are unconditional (a stage row always holds KC bytes; absent groups are
 // skipped at the DMMAs), the four tiles of a stage are unrolled with the next tile's operands
 // loaded ahead of the current tile's DMMAs, and full chunks run a branch-free instantiation.
+//
+// EX (MODE 11): C = 8 NCT + 1 classes. SeqUnwinder's label designs often are 2^k labels plus one
+// outgroup / "Random" class (BASELINE configs[3]: 16 + 1 = 17), and an fp64 MMA tile is 8 classes
+// wide, so a third class tile would issue 24 classes' worth of DMMAs for 17. The last class instead
+// rides along as plain DFMAs on operands the DMMA path has already converted: in pass 1 every lane
+// multiplies its count by the class's V entry of the same column (one DFMA per conversion, then a
+// 4-lane shuffle sum per row), in pass 2 by the class's residual of the same row (accumulators per
+// column, shuffle sum at the end of the chunk). One DFMA warp instruction costs the fp64 pipe 2
+// cycles against 16 for a DMMA: 17 classes cost 2 x 16 + 2 instead of 3 x 16 cycles per conversion.
 #pragma once
 
 #include "admm_eval_packed.cuh"
@@ -52,34 +61,36 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // Shared-memory carve-up (TileSmemLayout re-used): w = the solver's slice cache (one class tile
-// only), stage = kPcStages x (32 rows x KCS bytes | 32 x (Cp + 4) residual doubles: the row stride
-// Cp + 4 makes pass 2's fragment loads conflict-free), plog = [2][8 warps][32 rows][Cp] partial
-// logits, rs = 8 x Cp offset partials + Cp offsets + Cp class sums.
-inline TileSmemLayout packed_chunk_smem_layout(int Cp, size_t slice_bytes)
+// only), stage = kPcStages x (32 rows x KCS bytes | 32 residual rows of CL doubles at a stride that
+// makes pass 2's fragment loads conflict-free), plog = [2][8 warps][32 rows][CL] partial logits,
+// rs = 8 x CL offset partials + CL offsets + CL class sums. CL = 8 nct (+ 2 with the extra class).
+inline TileSmemLayout packed_chunk_smem_layout(int nct, bool extra, size_t slice_bytes)
 {
     TileSmemLayout L{};
-    const int nct = Cp / 8;
     const int KCS = nct == 1 ? PackedChunkCfg<1>::KCS : (nct == 2 ? PackedChunkCfg<2>::KCS : PackedChunkCfg<3>::KCS);
+    const int CL = 8 * nct + (extra ? 2 : 0), RS = CL + (extra ? 2 : 4);
     L.w_off = 0;
     L.w_bytes = (slice_bytes + 127) & ~(size_t)127;
     L.stage_off = L.w_bytes;
-    L.stage_bytes = (size_t)kPcRows * KCS + (size_t)kPcRows * (Cp + 4) * sizeof(double);
+    L.stage_bytes = (size_t)kPcRows * KCS + (size_t)kPcRows * RS * sizeof(double);
     L.plog_off = L.stage_off + (size_t)kPcStages * L.stage_bytes;
-    L.rs_off = L.plog_off + (size_t)2 * kDmmaWarps * kPcRows * Cp * sizeof(double);
-    L.bar_off = L.rs_off + (size_t)(kDmmaWarps * Cp + 2 * Cp) * sizeof(double);
+    L.rs_off = L.plog_off + (size_t)2 * kDmmaWarps * kPcRows * CL * sizeof(double);
+    L.bar_off = L.rs_off + (size_t)(kDmmaWarps * CL + 2 * CL) * sizeof(double);
     L.total = L.bar_off + 128;
     L.NS = kPcStages;
     return L;
 }
 
-template <int NCT>
+template <int NCT, bool EX = false>
 struct PackedChunkEval {
     static constexpr int NBG = PackedChunkCfg<NCT>::NBG, KC = PackedChunkCfg<NCT>::KC,
                          KCS = PackedChunkCfg<NCT>::KCS, CP = NCT * 8;
-    static constexpr int RS = CP + 4;                          // residual row stride in a stage (doubles)
+    static constexpr int CL = CP + (EX ? 2 : 0);               // doubles per logits / residual row; the
+                                                               // extra class is entry CP, entry CP + 1 is 0
+    static constexpr int RS = CL + (EX ? 2 : 4);               // residual row stride in a stage (4 or 12 mod 16)
     static constexpr int kHelpers = kThreads - kDmmaWarps * 32;  // 96 threads of the three helper warps
     static constexpr int kTiles = kPcRows / 8;
-    static constexpr unsigned kPlogHalf = (unsigned)kDmmaWarps * kPcRows * CP * 8;  // bytes of one plog buffer
+    static constexpr unsigned kPlogHalf = (unsigned)kDmmaWarps * kPcRows * CL * 8;  // bytes of one plog buffer
     const AdmmDev &P;
     int blk, cta, G;
     unsigned stage_s, plog_s;   // 32-bit shared addresses of stage 0 / the partial logits
@@ -133,8 +144,8 @@ struct PackedChunkEval {
         }
         if (with_res) {
             const unsigned rd = sb + (unsigned)(kPcRows * KCS);
-            const unsigned char *rsrc = reinterpret_cast<const unsigned char *>(Lb + (size_t)row0 * CP);
-            constexpr int per_row = CP / 2;   // 16-byte pieces of a residual row
+            const unsigned char *rsrc = reinterpret_cast<const unsigned char *>(Lb + (size_t)row0 * CL);
+            constexpr int per_row = CL / 2;   // 16-byte pieces of a residual row
 #pragma unroll
             for (int k = 0; k < (kPcRows * per_row + kHelpers - 1) / kHelpers; ++k) {
                 const int i = ht + k * kHelpers;
@@ -156,19 +167,19 @@ struct PackedChunkEval {
         const int row0 = r0 + st * kPcRows;
         const unsigned pl = plog_s + (unsigned)(st & 1) * kPlogHalf;
 #pragma unroll
-        for (int k = 0; k < (kPcRows * CP / 2 + kHelpers - 1) / kHelpers; ++k) {
+        for (int k = 0; k < (kPcRows * CL / 2 + kHelpers - 1) / kHelpers; ++k) {
             const int i = ht + k * kHelpers;
-            if (i < kPcRows * CP / 2) {
-                const int r = (2 * i) / CP, cc = 2 * i - r * CP;
+            if (i < kPcRows * CL / 2) {
+                const int r = (2 * i) / CL, cc = 2 * i - r * CL;
                 if (row0 + r < r1) {
                     double2 p[kDmmaWarps];
 #pragma unroll
                     for (int w8 = 0; w8 < kDmmaWarps; ++w8)
-                        p[w8] = lds_v2f64(pl + (unsigned)(((w8 * kPcRows + r) * CP + cc) * 8));
+                        p[w8] = lds_v2f64(pl + (unsigned)(((w8 * kPcRows + r) * CL + cc) * 8));
                     double2 v;
                     v.x = ((p[0].x + p[1].x) + (p[2].x + p[3].x)) + ((p[4].x + p[5].x) + (p[6].x + p[7].x));
                     v.y = ((p[0].y + p[1].y) + (p[2].y + p[3].y)) + ((p[4].y + p[5].y) + (p[6].y + p[7].y));
-                    double *lp = Lb + (size_t)(row0 + r) * CP + cc;
+                    double *lp = Lb + (size_t)(row0 + r) * CL + cc;
                     if (c == 0) {
                         __stcg(reinterpret_cast<double2 *>(lp), v);
                     } else {
@@ -182,9 +193,11 @@ struct PackedChunkEval {
 
     // DMMA warps, pass 1, one stage: partial logits of the four tiles over this warp's column groups.
     // sb = stage + lane offset (row gid, byte 4 qd + 16 warp); pw = this warp's plog slice + lane offset.
+    // EX: vex = the extra class's V entries of this lane's columns; its partial logit of row gid is
+    // the 4-lane sum of the lanes' DFMA chains, written by lane qd = 0 to entry CP of the row.
     template <bool FULL>
     __device__ __forceinline__ void pass1_stage(unsigned sb, unsigned pw, const double (&vreg)[NBG * 4][NCT],
-                                                int ngw) const
+                                                const double (&vex)[NBG * 4], int ngw) const
     {
         unsigned cur[NBG], nxt[NBG];
 #pragma unroll
@@ -198,6 +211,7 @@ struct PackedChunkEval {
                     nxt[i] = lds_u32(sb + (unsigned)((tt + 1) * 8 * KCS) + 128u * i);
             }
             double pa[NCT][2][2];
+            double ex0 = 0.0, ex1 = 0.0;
 #pragma unroll
             for (int ct = 0; ct < NCT; ++ct)
                 pa[ct][0][0] = pa[ct][0][1] = pa[ct][1][0] = pa[ct][1][1] = 0.0;
@@ -211,13 +225,26 @@ struct PackedChunkEval {
 #pragma unroll
                     for (int ct = 0; ct < NCT; ++ct)
                         dmma884(pa[ct][t & 1], xa, vreg[4 * i + t][ct]);
+                    if (EX) {
+                        if (t & 1)
+                            ex1 = fma(xa, vex[4 * i + t], ex1);
+                        else
+                            ex0 = fma(xa, vex[4 * i + t], ex0);
+                    }
                 }
             }
             // lane holds the partial S[row gid][class ct*8 + 2 qd + {0, 1}]
 #pragma unroll
             for (int ct = 0; ct < NCT; ++ct)
-                sts_v2f64(pw + (unsigned)((8 * tt * CP + ct * 8) * 8), pa[ct][0][0] + pa[ct][1][0],
+                sts_v2f64(pw + (unsigned)((8 * tt * CL + ct * 8) * 8), pa[ct][0][0] + pa[ct][1][0],
                           pa[ct][0][1] + pa[ct][1][1]);
+            if (EX) {
+                double e = ex0 + ex1;
+                e += __shfl_xor_sync(0xffffffffu, e, 1);
+                e += __shfl_xor_sync(0xffffffffu, e, 2);
+                if ((threadIdx.x & 3) == 0)   // pw points at classes 2 qd = 0 of row gid
+                    sts_v2f64(pw + (unsigned)((8 * tt * CL + CP) * 8), e, 0.0);
+            }
 #pragma unroll
             for (int i = 0; i < NBG; ++i)
                 cur[i] = nxt[i];
@@ -226,16 +253,24 @@ struct PackedChunkEval {
 
     // DMMA warps, pass 2, one stage: acc += R^T n over the four tiles.
     // sb = stage + lane offset (row qd, byte 2 gid + 16 warp); rb = residual rows + lane offset (row qd, class gid).
+    // EX: rx = residual rows + (row qd, entry CP); aex[i][h] accumulates the extra class's
+    // sum over this lane's rows of R[row][CP] n[row][16 g + 2 gid + h].
     template <bool FULL>
-    __device__ __forceinline__ void pass2_stage(unsigned sb, unsigned rb, double (&acc)[NBG][2][NCT][2],
+    __device__ __forceinline__ void pass2_stage(unsigned sb, unsigned rb, unsigned rx,
+                                                double (&acc)[NBG][2][NCT][2], double (&aex)[NBG][2],
                                                 int ngw) const
     {
         double a0[NCT], a1[NCT], na0[NCT], na1[NCT];
+        double e0 = 0.0, e1 = 0.0, ne0 = 0.0, ne1 = 0.0;
         unsigned x0[NBG], x1[NBG], nx0[NBG], nx1[NBG];
 #pragma unroll
         for (int ct = 0; ct < NCT; ++ct) {
             a0[ct] = na0[ct] = lds_f64(rb + (unsigned)(ct * 64));                  // R[row qd][class]
             a1[ct] = na1[ct] = lds_f64(rb + (unsigned)((4 * RS + ct * 8) * 8));    // R[row 4+qd][class]
+        }
+        if (EX) {
+            e0 = ne0 = lds_f64(rx);
+            e1 = ne1 = lds_f64(rx + (unsigned)(4 * RS * 8));
         }
 #pragma unroll
         for (int i = 0; i < NBG; ++i) {
@@ -249,6 +284,10 @@ struct PackedChunkEval {
                 for (int ct = 0; ct < NCT; ++ct) {
                     na0[ct] = lds_f64(rb + (unsigned)(((8 * tt + 8) * RS + ct * 8) * 8));
                     na1[ct] = lds_f64(rb + (unsigned)(((8 * tt + 12) * RS + ct * 8) * 8));
+                }
+                if (EX) {
+                    ne0 = lds_f64(rx + (unsigned)((8 * tt + 8) * RS * 8));
+                    ne1 = lds_f64(rx + (unsigned)((8 * tt + 12) * RS * 8));
                 }
 #pragma unroll
                 for (int i = 0; i < NBG; ++i) {
@@ -275,12 +314,20 @@ struct PackedChunkEval {
 #pragma unroll
                 for (int ct = 0; ct < NCT; ++ct)
                     dmma884(acc[i][1][ct], a1[ct], b11);
+                if (EX) {
+                    aex[i][0] = fma(e0, b00, aex[i][0]);
+                    aex[i][1] = fma(e0, b01, aex[i][1]);
+                    aex[i][0] = fma(e1, b10, aex[i][0]);
+                    aex[i][1] = fma(e1, b11, aex[i][1]);
+                }
             }
 #pragma unroll
             for (int ct = 0; ct < NCT; ++ct) {
                 a0[ct] = na0[ct];
                 a1[ct] = na1[ct];
             }
+            e0 = ne0;
+            e1 = ne1;
 #pragma unroll
             for (int i = 0; i < NBG; ++i) {
                 x0[i] = nx0[i];
@@ -295,18 +342,22 @@ struct PackedChunkEval {
         const int qd = lane & 3, gid = lane >> 2;
         const int dimp = P.dimp;
         const bool dmma_warp = warp < kDmmaWarps;
-        double *Lb = P.R + (size_t)blk * P.nb * CP;   // logits, then residuals, of this block's rows
-        double *so = scr;                               // [8 warps][CP] offset partials
-        double *o_all = scr + kDmmaWarps * CP;          // [CP] offsets o[c]
-        double *sc_all = o_all + CP;                    // [CP] class sums of the residuals
+        double *Lb = P.R + (size_t)blk * P.nb * CL;   // logits, then residuals, of this block's rows
+        double *so = scr;                               // [8 warps][CL] offset partials
+        double *o_all = scr + kDmmaWarps * CL;          // [CL] offsets o[c]
+        double *sc_all = o_all + CL;                    // [CL] class sums of the residuals
         // per-lane byte offsets into a stage / a plog slice (see pass1_stage / pass2_stage)
         const unsigned off1 = (unsigned)(gid * KCS + 4 * qd + 16 * warp);
         const unsigned off2 = (unsigned)(qd * KCS + 2 * gid + 16 * warp);
         const unsigned offr = (unsigned)(kPcRows * KCS + (qd * RS + gid) * 8);
-        const unsigned offp = (unsigned)(((warp * kPcRows + gid) * CP + 2 * qd) * 8);
-        if (dmma_warp && qd == 0)
+        const unsigned offx = (unsigned)(kPcRows * KCS + (qd * RS + CP) * 8);
+        const unsigned offp = (unsigned)(((warp * kPcRows + gid) * CL + 2 * qd) * 8);
+        if (dmma_warp && qd == 0) {
             for (int ct = 0; ct < NCT; ++ct)
-                so[warp * CP + ct * 8 + gid] = 0.0;
+                so[warp * CL + ct * 8 + gid] = 0.0;
+            if (EX && gid < 2)
+                so[warp * CL + CP + gid] = 0.0;
+        }
 
         // ---------------- pass 1: logits, chunk by chunk ----------------
         for (int c = 0; c < nch; ++c) {
@@ -314,9 +365,10 @@ struct PackedChunkEval {
             const int ngroups = wc >> 4;
             const int ngw = dmma_warp ? (ngroups - warp + kDmmaWarps - 1) / kDmmaWarps : 0;
             double vreg[NBG * 4][NCT];
+            double vex[NBG * 4];
             if (dmma_warp) {
                 // V fragments of this warp's column groups (constant for all tiles of the chunk)
-                double pb[NCT];
+                double pb[NCT], pbx = 0.0;
 #pragma unroll
                 for (int ct = 0; ct < NCT; ++ct)
                     pb[ct] = 0.0;
@@ -350,6 +402,25 @@ struct PackedChunkEval {
                         pb[ct] += m23.x * vreg[4 * i + 2][ct];
                         pb[ct] += m23.y * vreg[4 * i + 3][ct];
                     }
+                    if (EX) {
+                        // the extra class (index CP) at this lane's four columns: the same for all gid
+                        double2 w01 = make_double2(0.0, 0.0), w23 = w01;
+                        if (ok) {
+                            const double *wg = xcur + (size_t)CP * dimp + col;
+                            w01 = __ldcg(reinterpret_cast<const double2 *>(wg));
+                            w23 = __ldcg(reinterpret_cast<const double2 *>(wg + 2));
+                        }
+                        vex[4 * i + 0] = w01.x * s01.x;
+                        vex[4 * i + 1] = w01.y * s01.y;
+                        vex[4 * i + 2] = w23.x * s23.x;
+                        vex[4 * i + 3] = w23.y * s23.y;
+                        pbx += m01.x * vex[4 * i + 0];
+                        pbx += m01.y * vex[4 * i + 1];
+                        pbx += m23.x * vex[4 * i + 2];
+                        pbx += m23.y * vex[4 * i + 3];
+                    } else {
+                        vex[4 * i + 0] = vex[4 * i + 1] = vex[4 * i + 2] = vex[4 * i + 3] = 0.0;
+                    }
                 }
 #pragma unroll
                 for (int ct = 0; ct < NCT; ++ct) {
@@ -357,7 +428,13 @@ struct PackedChunkEval {
                     v += __shfl_xor_sync(0xffffffffu, v, 1);
                     v += __shfl_xor_sync(0xffffffffu, v, 2);
                     if (qd == 0)
-                        so[warp * CP + ct * 8 + gid] += v;   // this warp's own slot, summed over the chunks
+                        so[warp * CL + ct * 8 + gid] += v;   // this warp's own slot, summed over the chunks
+                }
+                if (EX) {
+                    pbx += __shfl_xor_sync(0xffffffffu, pbx, 1);
+                    pbx += __shfl_xor_sync(0xffffffffu, pbx, 2);
+                    if (lane == 0)
+                        so[warp * CL + CP] += pbx;
                 }
             } else {
                 if (nst > 0)
@@ -376,9 +453,9 @@ struct PackedChunkEval {
                         const unsigned sb = stage_addr(st) + off1;
                         const unsigned pw = plog_s + (unsigned)(st & 1) * kPlogHalf + offp;
                         if (full)
-                            pass1_stage<true>(sb, pw, vreg, ngw);
+                            pass1_stage<true>(sb, pw, vreg, vex, ngw);
                         else
-                            pass1_stage<false>(sb, pw, vreg, ngw);
+                            pass1_stage<false>(sb, pw, vreg, vex, ngw);
                     }
                 } else {
                     // helper warps: next fetch, then the logits of the PREVIOUS stage += its 8 K-slices
@@ -394,10 +471,10 @@ struct PackedChunkEval {
             }
         }
         // offsets o[c] = sum over the 8 warps' slots (fixed order)
-        if (threadIdx.x < CP) {
+        if (threadIdx.x < CL) {
             double s = 0.0;
             for (int w8 = 0; w8 < kDmmaWarps; ++w8)
-                s += so[w8 * CP + threadIdx.x];
+                s += so[w8 * CL + threadIdx.x];
             o_all[threadIdx.x] = s;
         }
         __syncthreads();
@@ -405,25 +482,25 @@ struct PackedChunkEval {
         // ---------------- softmax over my rows: logits -> residuals, NLL, class sums ----------------
         // (the logits were accumulated in L2 by RED: read them past L1)
         double facc = 0.0;
-        double rsum[CP];
+        double rsum[CL];
 #pragma unroll
-        for (int cc = 0; cc < CP; ++cc)
+        for (int cc = 0; cc < CL; ++cc)
             rsum[cc] = 0.0;
         {
             const int *yb = P.y + (size_t)blk * P.nb;
             const double *wb = P.w + (size_t)blk * P.nb;
             for (int row = r0 + threadIdx.x; row < r1; row += kThreads) {
-                double *lp = Lb + (size_t)row * CP;
-                double lv[CP];
+                double *lp = Lb + (size_t)row * CL;
+                double lv[CL];
                 double mx = -INFINITY;
 #pragma unroll
-                for (int cc = 0; cc < CP; cc += 2) {
+                for (int cc = 0; cc < CL; cc += 2) {
                     const double2 l2 = __ldcg(reinterpret_cast<const double2 *>(lp + cc));
                     lv[cc] = l2.x - o_all[cc];
                     lv[cc + 1] = l2.y - o_all[cc + 1];
                 }
 #pragma unroll
-                for (int cc = 0; cc < CP; ++cc)
+                for (int cc = 0; cc < CL; ++cc)
                     if (cc < P.C)
                         mx = fmax(mx, lv[cc]);
                 const int cls = yb[row];
@@ -431,13 +508,13 @@ struct PackedChunkEval {
                 const double lcls = __ldcg(lp + cls) - o_all[cls];
                 double den = 0.0;
 #pragma unroll
-                for (int cc = 0; cc < CP; ++cc) {
+                for (int cc = 0; cc < CL; ++cc) {
                     lv[cc] = (cc < P.C) ? exp(lv[cc] - mx) : 0.0;
                     den += lv[cc];
                 }
                 facc -= wi * ((lcls - mx) - log(den));
 #pragma unroll
-                for (int cc = 0; cc < CP; cc += 2) {
+                for (int cc = 0; cc < CL; cc += 2) {
                     double ra = 0.0, rb = 0.0;
                     if (cc < P.C) {
                         ra = wi * (lv[cc] / den);
@@ -456,7 +533,7 @@ struct PackedChunkEval {
             }
         }
 #pragma unroll
-        for (int cc = 0; cc < CP; ++cc) {
+        for (int cc = 0; cc < CL; ++cc) {
             const double s = block_sum(rsum[cc], red);   // (also orders the residual stores before pass 2)
             if (threadIdx.x == 0)
                 sc_all[cc] = s;
@@ -470,13 +547,16 @@ struct PackedChunkEval {
             const int ngroups = wc >> 4;
             const int ngw = dmma_warp ? (ngroups - warp + kDmmaWarps - 1) / kDmmaWarps : 0;
             double acc[NBG][2][NCT][2];
+            double aex[NBG][2];
 #pragma unroll
             for (int i = 0; i < NBG; ++i)
 #pragma unroll
-                for (int h = 0; h < 2; ++h)
+                for (int h = 0; h < 2; ++h) {
+                    aex[i][h] = 0.0;
 #pragma unroll
                     for (int ct = 0; ct < NCT; ++ct)
                         acc[i][h][ct][0] = acc[i][h][ct][1] = 0.0;
+                }
             if (!dmma_warp) {
                 if (nst > 0)
                     fetch(c, 0, true, Lb);
@@ -492,9 +572,9 @@ struct PackedChunkEval {
                 if (dmma_warp) {
                     const unsigned sa = stage_addr(st);
                     if (full)
-                        pass2_stage<true>(sa + off2, sa + offr, acc, ngw);
+                        pass2_stage<true>(sa + off2, sa + offr, sa + offx, acc, aex, ngw);
                     else
-                        pass2_stage<false>(sa + off2, sa + offr, acc, ngw);
+                        pass2_stage<false>(sa + off2, sa + offr, sa + offx, acc, aex, ngw);
                 } else {
                     if (st + 2 < nst)
                         fetch(c, st + 2, true, Lb);
@@ -527,6 +607,23 @@ struct PackedChunkEval {
                                 __stcg(dst + 1, make_double2((acc[i][0][ct][1] - m23.x * sc) * s23.x,
                                                              (acc[i][1][ct][1] - m23.y * sc) * s23.y));
                             }
+                        }
+                    }
+                    if (EX) {
+                        // extra class: the lanes of a quad hold the partial sums of rows qd, 4 + qd of
+                        // every tile for columns 16 g + 2 gid + {0, 1}; lane qd = 0 stores the total
+                        double v0 = aex[i][0], v1 = aex[i][1];
+                        v0 += __shfl_xor_sync(0xffffffffu, v0, 1);
+                        v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+                        v0 += __shfl_xor_sync(0xffffffffu, v0, 2);
+                        v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
+                        if (g < ngroups && qd == 0) {
+                            const int cx = c * KC + 16 * g + 2 * gid;
+                            const double2 sx = __ldg(reinterpret_cast<const double2 *>(P.cinvsd + cx));
+                            const double2 mx2 = __ldg(reinterpret_cast<const double2 *>(P.cmean + cx));
+                            const double sc = sc_all[CP];
+                            __stcg(reinterpret_cast<double2 *>(gp + (size_t)CP * dimp + cx),
+                                   make_double2((v0 - mx2.x * sc) * sx.x, (v1 - mx2.y * sc) * sx.y));
                         }
                     }
                 }

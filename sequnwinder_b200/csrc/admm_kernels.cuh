@@ -44,6 +44,8 @@ __device__ __forceinline__ int ld_volatile_int(const int *p)
 //           evaluation (PackedEval): count matrices with rows up to 768 columns and C <= 8.
 //   MODE 10 packed counts streamed as byte tiles (cp.async), column-chunked, two passes: count
 //           matrices of any row length, up to 24 classes, blocks of any size (cfg-3, cfg-4).
+//   MODE 11 MODE 10 for C = 8 NCT + 1 classes (2^k labels + one outgroup class, cfg-4): NCT class
+//           tiles of DMMAs and the last class as DFMAs on the operands the DMMA path converted.
 //   MODE 9  MODE 8 with two CTAs of 192 threads per SM (4 DMMA + 2 helper warps each): the CTAs of
 //           an SM belong to different ADMM blocks, so one evaluates while the other sits in its
 //           solver's exchange chain.
@@ -88,6 +90,10 @@ struct EvalSelect<NCT, 8> {   // packed counts resident in shared memory (admm_e
 template <int NCT>
 struct EvalSelect<NCT, 10> {  // packed counts streamed from HBM, column-chunked (admm_eval_packed_chunk.cuh)
     typedef PackedChunkEval<NCT> type;
+};
+template <int NCT>
+struct EvalSelect<NCT, 11> {  // the same for C = 8 NCT + 1 classes: the last class rides along as DFMAs
+    typedef PackedChunkEval<NCT, true> type;
 };
 template <int NCT>
 struct EvalSelect<NCT, 9> {   // the same with two CTAs of 192 threads per SM
@@ -371,7 +377,7 @@ admm_xupdate_kernel(AdmmDev P, TileSmemLayout L, int phase, int eval_cap)
     ws.cta = cta;
     ws.prof = P.prof ? s_prof : nullptr;
     // modes 4/5 keep W in registers: the head of the dynamic shared memory is the slice cache
-    ws.slice = ((MODE == 4 || MODE == 5 || MODE == 8 || MODE == 9 || MODE == 10) && NCT == 1)
+    ws.slice = ((MODE == 4 || MODE == 5 || MODE == 8 || MODE == 9 || MODE == 10 || MODE == 11) && NCT == 1)
                    ? reinterpret_cast<double *>(smem_raw) : nullptr;
     int status = 0;
     bool finished = false;
@@ -902,7 +908,7 @@ admm_eval_kernel(AdmmDev P, TileSmemLayout L, double pho, double *f_out)
     BlockProblem<Eval> prob{P, blk, cta, P.G, pho, P.ut + (size_t)blk * P.upad, ev,
                             P.leaf_edge_ptr, P.edge_par};
     double fpart = prob.eval_partial(xt);
-    if (MODE == 4 || MODE == 5 || MODE == 6 || MODE == 8 || MODE == 9 || MODE == 10) {
+    if (MODE == 4 || MODE == 5 || MODE == 6 || MODE == 8 || MODE == 9 || MODE == 10 || MODE == 11) {
         // further evaluations exercise the ring wrap-around / resident path; results must agree
         for (int rep = 0; rep < 2; ++rep) {
             __syncthreads();

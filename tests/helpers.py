@@ -30,10 +30,11 @@ class Problem:
 
 
 def make_problem(cfg: str = "cfg1", n_sites: int | None = None, max_features: int | None = None,
-                 seed_offset: int = 0) -> Problem:
+                 seed_offset: int = 0, outgroup: bool | None = None) -> Problem:
     c = synth.CONFIGS[cfg]
     d = synth.generate(n_sites or c["n_sites"], c["n_labels"],
-                       seed=synth.SEED_BASE + int(cfg[-1]) + seed_offset, outgroup=c["outgroup"])
+                       seed=synth.SEED_BASE + int(cfg[-1]) + seed_offset,
+                       outgroup=c["outgroup"] if outgroup is None else outgroup)
     counts, has_n = O.kmer_count(d.bases, d.offsets, c["kmin"], c["kmax"])
     assert not has_n.any()
     des = structure.make_design(d.annotations)

@@ -574,9 +574,9 @@ def test_packed_chunk_evaluation_matches_oracle(oracle, monkeypatch, cfg, n, mf,
 @pytest.mark.parametrize("cfg,n,mf,T,A,S,force", [
     ("cfg1", 500, 60, 5, 50, 3, True),       # one class tile, forced onto the streamed path
     ("cfg2", 4000, None, 8, 4, 1, True),
-    ("cfg4", 1700, 200, 4, 6, 2, False),     # 17 leaves (three class tiles) incl. parentless Random
+    ("cfg4", 1700, 200, 4, 6, 2, True),      # 17 leaves as three class tiles (the padded form, forced)
     ("cfg3", 2400, None, 8, 2, 1, False),    # k = 4..7: 10 921 columns, C = 12 (two class tiles, 22 chunks)
-    ("cfg4", 3400, None, 8, 2, 1, False),    # k = 4..6: 2 729 columns, C = 17
+    ("cfg4", 3400, None, 8, 2, 1, True),     # k = 4..6: 2 729 columns, C = 17, padded form
 ])
 def test_packed_chunk_trainer_matches_oracle(oracle, monkeypatch, cfg, n, mf, T, A, S, force):
     if force:
@@ -586,6 +586,53 @@ def test_packed_chunk_trainer_matches_oracle(oracle, monkeypatch, cfg, n, mf, T,
                                       num_threads=T, admm_max_itr=A, nodes_max_itr=S, host_threads=8)
     lo = run_gpu(p, T, A, S, packed=True)
     assert lo.stats.eval_mode == 10
+    assert lo.log.admm_iters == tr.admm_iters
+    assert np.array_equal(lo.log.nfev, tr.log_nfev[:, opt.java_block_order(T)])
+    assert _rel(lo.getX(), xo) <= REL_TOL
+    assert _rel(lo.getsmX(), smo) <= REL_TOL
+
+
+# --------------------------------------------------------------------------------------------
+# MODE 11: C = 8 n + 1 classes (2^k labels + one outgroup class: 16 + Random at cfg-4, 8 + Random
+# here): n class tiles of DMMAs, the last class as DFMAs on the operands the DMMA path converted.
+# --------------------------------------------------------------------------------------------
+def _extra_class_problem(cfg, n, mf):
+    p = make_problem(cfg, n, max_features=mf, outgroup=True)
+    assert p.num_classes in (9, 17)
+    return p
+
+
+@pytest.mark.parametrize("cfg,n,mf,T", [("cfg4", 1700, 200, 4), ("cfg4", 3400, None, 8),
+                                          ("cfg2", 3000, None, 8), ("cfg2", 900, 100, 5)])
+def test_extra_class_evaluation_matches_oracle(oracle, cfg, n, mf, T):
+    p = _extra_class_problem(cfg, n, mf)
+    nrow, dim = p.data.shape
+    C, NN = p.num_classes, p.st.num_nodes
+    rng = np.random.default_rng(7)
+    cx = rng.normal(size=(T, C * dim)) * 0.05
+    smx = rng.normal(size=NN * dim) * 0.05
+    f, g = opt.block_evaluate(None, p.cls, p.weights, p.crs, C, T, cx, smx, 1.7, counts=packed_counts(p))
+    nb = nrow // T
+    zd = np.zeros(NN * NN * dim)
+    for b, t in enumerate(opt.java_block_order(T)):
+        rows = np.arange(nb) * T + t
+        fo, go = oracle.eval_fg(p.data[rows], p.cls[rows], p.weights[rows], cx[b], smx, zd, zd, 1.7,
+                                p.st, C)
+        assert abs(f[b] - fo) <= 1e-12 * abs(fo)
+        assert np.abs(g[b] - go).max() <= 1e-12 * np.abs(go).max()
+
+
+@pytest.mark.parametrize("cfg,n,mf,T,A,S", [
+    ("cfg4", 1700, 200, 4, 6, 2),      # 17 leaves incl. the parentless Random leaf: 2 class tiles + 1
+    ("cfg4", 3400, None, 8, 2, 1),     # k = 4..6: 2 729 columns, 8 chunks
+    ("cfg2", 3000, None, 8, 3, 1),     # 8 ring labels + Random = 9: 1 class tile + 1 (slice cache in use)
+])
+def test_extra_class_trainer_matches_oracle(oracle, cfg, n, mf, T, A, S):
+    p = _extra_class_problem(cfg, n, mf)
+    xo, smo, tr = oracle.lone_execute(p.x0, p.smx0, p.data, p.cls, p.weights, p.st, p.num_classes,
+                                      num_threads=T, admm_max_itr=A, nodes_max_itr=S, host_threads=8)
+    lo = run_gpu(p, T, A, S, packed=True)
+    assert lo.stats.eval_mode == 11
     assert lo.log.admm_iters == tr.admm_iters
     assert np.array_equal(lo.log.nfev, tr.log_nfev[:, opt.java_block_order(T)])
     assert _rel(lo.getX(), xo) <= REL_TOL
