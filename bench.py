@@ -803,6 +803,20 @@ def run_big(args, info, world, dev, comm, dist, torch):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the NCCL communicator is created once per process and shared by every trainer handle
+    # (sqw_admm_set_comm caches it by ncclUniqueId): time it apart from the per-training stages
+    comm_s = 0.0
+    if comm is not None:
+        from sequnwinder_b200 import _lib as _l
+        import ctypes as _C
+        t0 = time.time()
+        hh = _C.c_void_p()
+        _l.check(_l.load().sqw_admm_create(_C.byref(hh)))
+        _l.check(_l.load().sqw_admm_set_comm(hh, comm[0], comm[1], (_C.c_uint8 * 128).from_buffer_copy(comm[2])))
+        _l.load().sqw_admm_destroy(hh)
+        torch.cuda.synchronize()
+        comm_s = time.time() - t0
+
     lo = LOneCuda(x0.copy(), smx0.copy(), None)
     lo.setCountMatrixDevice(counts_t, plan.keep_idx, plan.mean, plan.sd, y_t, w_t, sites, rows_local=True)
     lo.setRidge(RIDGE); lo.setADMMmaxItrs(A); lo.setBGFSmaxItrs(-1); lo.setSeqUnwinderMaxIts(1)
@@ -897,7 +911,8 @@ def run_big(args, info, world, dev, comm, dist, torch):
         "evals_per_step": evals_all / args.steps, "block_evals_per_s": evals_all / admm_s,
         "ms_per_admm_iteration": admm_s / max(1, iters) * 1e3,
         "pipeline_s": {"host_setup": t_setup, "kmer_count_device": kmer_s,
-                       "column_plan_device": plan_s, "counts_to_training_matrix": build_s},
+                       "column_plan_device": plan_s, "counts_to_training_matrix": build_s,
+                       "nccl_comm_init_once_per_process": comm_s},
         "kmer_gbases_per_s": sites * LENGTH / kmer_s / 1e9,
         "kmer_roofline": {"bound": "hbm", "achieved": sites * (LENGTH + 4 * kc.numK) / kmer_s / 1e9 / world,
                           "peak": peak, "unit": "GB/s",

@@ -21,6 +21,8 @@
 #include "kmer_pack.cuh"
 
 #include <algorithm>
+#include <condition_variable>
+#include <functional>
 #include <cstdlib>
 #include <map>
 #include <mutex>
@@ -606,6 +608,69 @@ static void expand_range(const uint8_t *stage, int64_t a, int64_t b, const int32
     }
 }
 
+// Host threads of the expansion: created once per process and parked on a condition variable
+// (creating 15 threads per call cost a cfg-2 call up to a third of its 1.6 - 3 ms). One job at a
+// time; worker t of the first nt takes part in a job.
+class ExpandPool {
+public:
+    explicit ExpandPool(int n)
+    {
+        for (int t = 0; t < n; ++t)
+            workers_.emplace_back([this, t] { loop(t); });
+    }
+    ~ExpandPool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_work_.notify_all();
+        for (auto &w : workers_)
+            w.join();
+    }
+    int size() const { return (int)workers_.size(); }
+    template <class F>
+    void run(int nt, const F &f)
+    {
+        std::lock_guard<std::mutex> one_job(job_mu_);
+        std::unique_lock<std::mutex> lk(mu_);
+        job_ = [&f](int t) { f(t); };
+        active_ = nt;
+        pending_ = nt;
+        ++generation_;
+        cv_work_.notify_all();
+        cv_done_.wait(lk, [this] { return pending_ == 0; });
+        job_ = nullptr;
+    }
+
+private:
+    void loop(int t)
+    {
+        unsigned long long seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_work_.wait(lk, [&] { return stop_ || generation_ != seen; });
+            if (stop_)
+                return;
+            seen = generation_;
+            if (t >= active_)
+                continue;
+            lk.unlock();
+            job_(t);           // (job_ stays valid until pending_ reaches 0)
+            lk.lock();
+            if (--pending_ == 0)
+                cv_done_.notify_one();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex mu_, job_mu_;
+    std::condition_variable cv_work_, cv_done_;
+    std::function<void(int)> job_;
+    int active_ = 0, pending_ = 0;
+    unsigned long long generation_ = 0;
+    bool stop_ = false;
+};
+
 // `rows` compact rows into the caller's dense int32 rows on host threads: at least 2 MB of dense
 // output per thread, and one core left to the thread that drives the GPU (measured on the pool's
 // 16-core hosts, cfg-2: 1.6 ms per call with 15 threads, 1.7 with 16, 2.5 with 8).
@@ -614,21 +679,17 @@ static void expand_rows(const uint8_t *stage, int64_t rows, const std::vector<in
 {
     const int ncanon = (int)canon.size();
     const int64_t bytes = rows * numK * 4;
-    const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
-    const int nt = (int)std::min<int64_t>(std::min(31u, hw - 1), std::max<int64_t>(1, bytes >> 21));
-    auto work = [&](int64_t a, int64_t b) {
-        std::vector<int32_t> scratch;
-        expand_range(stage, a, b, canon.data(), ncanon, numK, out, scratch);
-    };
+    static ExpandPool pool((int)std::min(31u, std::max(2u, std::thread::hardware_concurrency()) - 1));
+    const int nt = (int)std::min<int64_t>(pool.size(), std::max<int64_t>(1, bytes >> 21));
     if (nt <= 1) {
-        work(0, rows);
+        std::vector<int32_t> scratch;
+        expand_range(stage, 0, rows, canon.data(), ncanon, numK, out, scratch);
         return;
     }
-    std::vector<std::thread> th;
-    for (int t = 0; t < nt; ++t)
-        th.emplace_back(work, rows * t / nt, rows * (t + 1) / nt);
-    for (auto &x : th)
-        x.join();
+    pool.run(nt, [&](int t) {
+        thread_local std::vector<int32_t> scratch;
+        expand_range(stage, rows * t / nt, rows * (t + 1) / nt, canon.data(), ncanon, numK, out, scratch);
+    });
 }
 
 static int host_kmer_count(const char *bases, const int64_t *offsets, int64_t n, int64_t max_len,
