@@ -36,9 +36,11 @@ extern "C" {
 /* Environment hooks read by the library (none is needed in production; defaults in brackets):
  *   tests      SQW_ADMM_EVAL_MODE=1|2|6   force a more general fp64 evaluation path
  *              SQW_ADMM_NO_PACKED=1       count matrices always through the fp64 kernels
- *              SQW_ADMM_PACKED_MODE=9|10  packed counts with two CTAs per SM (built, measured slower) /
- *                                         always through the streamed packed kernels (what long rows,
- *                                         more than 8 classes and budgeted handles use anyway)
+ *              SQW_ADMM_PACKED_MODE=9|10|12  packed counts with two CTAs per SM (built, measured slower) /
+ *                                         always through the column-chunked streamed kernels (what long
+ *                                         rows and more than 8 classes use anyway) / always panel by
+ *                                         panel (what short rows that do not fit shared memory use)
+ *              SQW_ADMM_PANEL_ROWS=n      MODE 12: at most n rows per panel [as many as fit]
  *              SQW_ADMM_UNFUSED=1         iteration tail as separate kernels / two collectives
  *   profiling  SQW_ADMM_PROFILE=1         per-phase timers of the x-update kernel on stderr
  *              SQW_ADMM_TAIL_PROFILE=1    multi-GPU: events between the kernels of the iteration tail
@@ -136,10 +138,11 @@ int sqw_admm_set_problem_dev(sqw_admm *h, int64_t n_rows, int32_t dim, int32_t n
  * rows_local = 1 (multi-GPU, sqw_admm_set_comm): they hold only the rows of this rank's blocks,
  * i.e. the rows i < floor(n_rows / T) * T with (i mod T) mod world == rank in ascending order of i,
  * so that every rank featurises its own sequences only (mean / sd stay the statistics of ALL rows).
- * Two packed kernels cover every shape: where a CTA's rows of its block fit shared memory (up to 8
- * classes, rows up to 768 columns: BASELINE configs[0..1]) they stay there for the whole launch;
- * otherwise (longer rows, up to 24 classes, blocks of any size: configs[2..3], and handles with a
- * CTA budget) they are streamed as byte tiles, column chunk by column chunk. The
+ * The packed kernels cover every shape. Up to 8 classes and rows up to 768 columns (BASELINE
+ * configs[0..1]): a CTA's rows of its block stay in shared memory for the whole launch where they
+ * fit, and pass through the same buffer panel by panel where they do not (handles with a CTA
+ * budget, blocks of many rows). Longer rows, up to 24 classes (configs[2..3]):
+ * streamed as byte tiles, column chunk by column chunk. The
  * call always succeeds for valid counts. Counts above 255 -> SQW_ERR_UNSUPPORTED. Synchronises
  * `stream`. */
 int sqw_admm_set_problem_counts(sqw_admm *h, int64_t n_rows, int32_t dim, int32_t num_classes,
@@ -214,9 +217,11 @@ typedef struct {
     /* which evaluation path ran (tests assert that the path a benchmark uses is the path they
      * compared with the oracle): */
     int32_t eval_mode;        /* 4/5 fp64 single-pass TMA tiles, 6 fp64 column-chunked, 1/2 fp64
-                                 streaming, 8/9 packed-count (uint8) tiles */
+                                 streaming, 8/9 packed counts (uint8) resident in shared memory,
+                                 12 the same panel by panel, 10/11 packed counts column-chunked */
     int32_t ctas_per_block;   /* CTAs of a block's group while every local block is active */
-    int32_t ring_stages;      /* tile stages of the TMA ring in shared memory */
+    int32_t ring_stages;      /* tile stages of the TMA ring in shared memory (8 / 12: 8-row tiles of
+                                 the row buffer = one panel) */
     int32_t tiles_per_cta;    /* tiles a CTA walks per evaluation pass; > ring_stages means the
                                  ring streams (refill path), <= means its rows stay resident */
 } sqw_admm_stats;

@@ -183,6 +183,7 @@ static XKernel xupdate_kernel(int nct, int mode)
     case 32 + 10: return admm_xupdate_kernel<2, 10>;
     case 48 + 10: return admm_xupdate_kernel<3, 10>;
     case 16 + 11: return admm_xupdate_kernel<1, 11>;
+    case 16 + 12: return admm_xupdate_kernel<1, 12>;
     case 32 + 11: return admm_xupdate_kernel<2, 11>;
     case 16 + 1: return admm_xupdate_kernel<1, 1>;
     case 16 + 2: return admm_xupdate_kernel<1, 2>;
@@ -210,6 +211,7 @@ static EKernel eval_kernel(int nct, int mode)
     case 32 + 10: return admm_eval_kernel<2, 10>;
     case 48 + 10: return admm_eval_kernel<3, 10>;
     case 16 + 11: return admm_eval_kernel<1, 11>;
+    case 16 + 12: return admm_eval_kernel<1, 12>;
     case 32 + 11: return admm_eval_kernel<2, 11>;
     case 16 + 1: return admm_eval_kernel<1, 1>;
     case 16 + 2: return admm_eval_kernel<1, 2>;
@@ -301,7 +303,7 @@ static int prepare(sqw_admm *h)
         n_sm = std::min(n_sm, h->cta_budget);
     const int mode = h->eval_mode;
     const size_t w_bytes = (size_t)D.Cp * D.wstride * sizeof(double);
-    if (mode == 4 || mode == 5 || mode == 6 || mode == 8 || mode == 9 || mode == 10 || mode == 11)
+    if (mode == 4 || mode == 5 || mode == 6 || mode == 8 || mode == 9 || mode == 10 || mode == 11 || mode == 12)
         h->xupdate_smem = h->layout.total;
     else if (mode == 1)
         h->xupdate_smem = w_bytes;
@@ -934,11 +936,27 @@ static int plan_blocks(sqw_admm *h, int64_t n_rows, int32_t dim, int32_t num_cla
             const int gmin = std::min(G, gcap);
             const int rows_cap8 = (int)((tiles + gmin - 1) / gmin) * 8;
             TileSmemLayout Lp = packed_smem_layout(dimp16, rows_cap8, kSolveSliceBytes);
-            if (Lp.total <= budget) {
+            const bool force12 = force && atoi(force) == 12;   // test hook: panels even where the rows fit
+            if (Lp.total <= budget && !force12) {
                 h->eval_mode = 8;
                 h->layout = Lp;
                 D.dimp = dimp16;
                 D.rsq = dimp16;
+            } else {
+                // MODE 12: the CTA's rows pass through the resident form's buffer panel by panel; the
+                // panel is as large as shared memory allows (SQW_ADMM_PANEL_ROWS: test hook, smaller)
+                int cap = rows_cap8;
+                if (const char *pr = getenv("SQW_ADMM_PANEL_ROWS"))
+                    cap = std::min(cap, std::max(8, atoi(pr) / 8 * 8));
+                while (cap > 8 && packed_smem_layout(dimp16, cap, kSolveSliceBytes).total > budget)
+                    cap -= 8;
+                Lp = packed_smem_layout(dimp16, cap, kSolveSliceBytes);
+                if (Lp.total <= budget) {
+                    h->eval_mode = 12;
+                    h->layout = Lp;
+                    D.dimp = dimp16;
+                    D.rsq = dimp16;
+                }
             }
         }
     }
@@ -1066,7 +1084,7 @@ static int build_from_counts(sqw_admm *h, const SrcT *d_src, long long src_strid
     admm_packed_stats_kernel<<<(D.dimp + 255) / 256, 256, 0, st>>>(d_mean, d_sd, d_col_idx, D.dim, D.dimp,
                                                                    mean_p, invsd_p, mean_f, sd_f);
     const int grid = (int)std::min<size_t>(rows, 148 * 16);
-    if (h->eval_mode == 8 || h->eval_mode == 9 || h->eval_mode == 10 || h->eval_mode == 11) {
+    if (h->eval_mode == 8 || h->eval_mode == 9 || h->eval_mode == 10 || h->eval_mode == 11 || h->eval_mode == 12) {
         unsigned char *dXq = nullptr;
         if ((rc = h->dalloc(&dXq, rows * D.rsq + 16384, false)) != SQW_OK) return rc;
         admm_gather_counts_kernel<SrcT, true><<<grid, 256, 0, st>>>(

@@ -118,12 +118,115 @@ __device__ __forceinline__ void sts_v2f64(unsigned a, double x, double y)
     asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) : "memory");
 }
 
-// DW = DMMA warps per CTA (8: one CTA per SM, 352 threads; 4: two CTAs per SM, 192 threads), NT = threads
-template <int NCT, int DW = 8, int NT = kThreads>
+// Pass 1 over `nt` 8-row tiles of byte rows at shared address rows_s (row stride rsq bytes, tile
+// stride tstride): this warp's partial logits of every tile -> shared memory at plw (one tile =
+// 8 rows x 8 classes). One shared address per lane and tile, immediate offsets for the warp's
+// groups; the loads are unconditional (an absent group reads bytes of the next row or, past the
+// last row, of the partial-logit buffer: multiplied by a zero V fragment) and the next tile's
+// words are in flight while this tile's DMMAs issue.
+template <int DW, int NBG>
+__device__ __forceinline__ void packed_pass1_tiles(const double (&wreg)[NBG * 4], unsigned rows_s, unsigned plw,
+                                                   unsigned tstride, int nt, int ngw)
+{
+    unsigned cur[NBG], nxt[NBG];
+#pragma unroll
+    for (int i = 0; i < NBG; ++i)
+        cur[i] = nxt[i] = (nt > 0) ? lds_u32(rows_s + 16u * DW * i) : 0u;
+#pragma unroll 2
+    for (int j = 0; j < nt; ++j) {
+        const unsigned nb_ = rows_s + (unsigned)min(j + 1, nt - 1) * tstride;
+#pragma unroll
+        for (int i = 0; i < NBG; ++i)
+            nxt[i] = lds_u32(nb_ + 16u * DW * i);
+        double pa[4][2];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            pa[c][0] = pa[c][1] = 0.0;
+#pragma unroll
+        for (int i = 0; i < NBG; ++i) {
+            if (i >= NBG - 2 && i >= ngw)  // warp-uniform; an absent earlier group multiplies zeros
+                break;
+            dmma884(pa[0], cvt_byte(cur[i], 0), wreg[4 * i + 0]);
+            dmma884(pa[1], cvt_byte(cur[i], 1), wreg[4 * i + 1]);
+            dmma884(pa[2], cvt_byte(cur[i], 2), wreg[4 * i + 2]);
+            dmma884(pa[3], cvt_byte(cur[i], 3), wreg[4 * i + 3]);
+        }
+        // lane holds the partial S[row gid][class 2 qd + {0, 1}]
+        sts_v2f64(plw + (unsigned)(kTileRows * 8 * 8) * j, (pa[0][0] + pa[1][0]) + (pa[2][0] + pa[3][0]),
+                  (pa[0][1] + pa[1][1]) + (pa[2][1] + pa[3][1]));
+#pragma unroll
+        for (int i = 0; i < NBG; ++i)
+            cur[i] = nxt[i];
+    }
+}
+
+// Pass 2 over the same tiles: acc += R^T n for HG column groups of this warp (group index gbase + i
+// of the warp's NBG), residual rows at rs_ (8 x 8 doubles per tile), byte rows at xs_.
+template <int DW, int NBG, int HG>
+__device__ __forceinline__ void packed_pass2_tiles(double (&acc)[HG][2][2], unsigned rs_, unsigned xs_, unsigned half,
+                                                   unsigned tstride, int nt, int gbase, int ngw)
+{
+    double a0 = lds_f64(rs_), a1 = lds_f64(rs_ + 4 * 8 * 8), na0 = a0, na1 = a1;
+    unsigned x0[HG], x1[HG], nx0[HG], nx1[HG];
+#pragma unroll
+    for (int i = 0; i < HG; ++i) {
+        x0[i] = nx0[i] = lds_u16(xs_ + 16u * DW * i);
+        x1[i] = nx1[i] = lds_u16(xs_ + half + 16u * DW * i);
+    }
+#pragma unroll 2
+    for (int j = 0; j < nt; ++j) {
+        // operands of the next tile (clamped on the last) ahead of this tile's DMMAs
+        const int jn = min(j + 1, nt - 1);
+        const unsigned rn = rs_ + (unsigned)(kTileRows * 8 * 8) * jn, xn = xs_ + tstride * jn;
+        na0 = lds_f64(rn);                  // R[row qd][class gid]
+        na1 = lds_f64(rn + 4 * 8 * 8);      // R[row 4+qd][class gid]
+#pragma unroll
+        for (int i = 0; i < HG; ++i) {
+            nx0[i] = lds_u16(xn + 16u * DW * i);
+            nx1[i] = lds_u16(xn + half + 16u * DW * i);
+        }
+        // rows 0..3 of every group first, then rows 4..7: an accumulator is re-used at a
+        // distance of 2 HG DMMAs (latency 26 cycles, issue 16)
+#pragma unroll
+        for (int i = 0; i < HG; ++i) {
+            if (gbase + i >= NBG - 2 && gbase + i >= ngw)  // warp-uniform
+                break;
+            dmma884(acc[i][0], a0, cvt_byte(x0[i], 0));
+            dmma884(acc[i][1], a0, cvt_byte(x0[i], 1));
+        }
+#pragma unroll
+        for (int i = 0; i < HG; ++i) {
+            if (gbase + i >= NBG - 2 && gbase + i >= ngw)
+                break;
+            dmma884(acc[i][0], a1, cvt_byte(x1[i], 0));
+            dmma884(acc[i][1], a1, cvt_byte(x1[i], 1));
+        }
+        a0 = na0;
+        a1 = na1;
+#pragma unroll
+        for (int i = 0; i < HG; ++i) {
+            x0[i] = nx0[i];
+            x1[i] = nx1[i];
+        }
+    }
+}
+
+// DW = DMMA warps per CTA (8: one CTA per SM, 352 threads; 4: two CTAs per SM, 192 threads), NT = threads.
+// STREAM (MODE 12): the CTA owns more rows than its shared memory holds (a CTA budget below the
+// whole GPU: concurrent sweeps and cross-validation folds; blocks of many short rows). The rows
+// then pass through the same buffer PANEL by panel - cap8 rows per bulk load from L2 / HBM, the
+// three phases on the panel, the gradient accumulators staying in registers across the panels - so
+// the inner loops are those of the resident form and every byte is fetched once per evaluation
+// (the column-chunked MODE 10 fetches twice and pays per 32-row stage). The first panel of the
+// next evaluation is fetched behind the solver's exchange chain; one panel = the resident form.
+template <int NCT, int DW = 8, int NT = kThreads, bool STREAM = false>
 struct PackedEval {
     static_assert(NCT == 1, "packed evaluation: one class tile");
     static constexpr int NBG = kPackedMaxGroups / DW;   // 16-column groups per DMMA warp
     static constexpr int kDmmaWarps = DW, kWarps = NT / 32, kThreads = NT;
+    static constexpr int HG = 6, NH = NBG / HG;         // pass 2: column groups per sweep, sweeps
+    static_assert(NBG % HG == 0, "column groups per warp");
+    static_assert(!STREAM || NH == 1, "panels keep one sweep's accumulators in registers");
     const AdmmDev &P;
     int blk, cta, G;
     unsigned char *rows;
@@ -134,6 +237,25 @@ struct PackedEval {
     int cap8, r0, r1, ntiles, rsq;
     bool loaded;
     long long *prof;
+    // STREAM: panels of cap8 rows; `have` = the panel in (or on its way into) the buffer, `inflight` =
+    // its load has not been waited for yet, `par` = mbarrier phase parity of that load
+    int npan, have;
+    bool inflight;
+    unsigned par;
+
+    // thread 0: bulk-load panel p of the CTA's rows (contiguous in the block-major matrix)
+    __device__ __forceinline__ void load_panel(int p)
+    {
+        const int pr0 = r0 + p * cap8;
+        const unsigned total = (unsigned)min(cap8, r1 - pr0) * (unsigned)rsq;
+        const unsigned char *src = P.Xq + ((size_t)blk * P.nb + pr0) * rsq;
+        // the buffer was read through the generic proxy (LDS) until the last __syncthreads
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&full[0], total);
+        constexpr unsigned kChunk = 16384;
+        for (unsigned o = 0; o < total; o += kChunk)
+            bulk_g2s_plain(rows + o, src + o, min(kChunk, total - o), &full[0]);
+    }
 
     __device__ void init(unsigned char *smem, const TileSmemLayout &L, double *red_)
     {
@@ -152,22 +274,30 @@ struct PackedEval {
         ntiles = max(0, (r1 - r0 + kTileRows - 1) / kTileRows);
         loaded = false;
         prof = nullptr;
+        npan = STREAM ? (max(0, r1 - r0) + cap8 - 1) / cap8 : 1;
+        have = 0;
+        inflight = STREAM && npan > 0;
+        par = 0u;
         // constant for the launch: the column statistics and this CTA's instance weights / classes
         for (int i = threadIdx.x; i < rsq; i += kThreads) {
             smean[i] = __ldg(P.cmean + i);
             sinvsd[i] = __ldg(P.cinvsd + i);
         }
-        for (int i = threadIdx.x; i < ntiles * kTileRows; i += kThreads) {
-            const bool rv = r0 + i < r1;
-            sw[i] = rv ? __ldg(P.w + (size_t)blk * P.nb + r0 + i) : 0.0;
-            sy[i] = rv ? __ldg(P.y + (size_t)blk * P.nb + r0 + i) : -1;
-        }
+        if (!STREAM)
+            for (int i = threadIdx.x; i < ntiles * kTileRows; i += kThreads) {
+                const bool rv = r0 + i < r1;
+                sw[i] = rv ? __ldg(P.w + (size_t)blk * P.nb + r0 + i) : 0.0;
+                sy[i] = rv ? __ldg(P.y + (size_t)blk * P.nb + r0 + i) : -1;
+            }
         if (threadIdx.x == 0) {
             mbar_init(&full[0], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
-        if (threadIdx.x == 0 && ntiles > 0) {
+        if (STREAM) {
+            if (threadIdx.x == 0 && npan > 0)
+                load_panel(0);
+        } else if (threadIdx.x == 0 && ntiles > 0) {
             // the CTA's rows are contiguous in the block-major matrix: a few large bulk copies
             const unsigned total = (unsigned)(r1 - r0) * (unsigned)rsq;
             const unsigned char *src = P.Xq + ((size_t)blk * P.nb + r0) * rsq;
@@ -182,12 +312,135 @@ struct PackedEval {
 
     __device__ void drain()
     {
-        if (!loaded && ntiles > 0)
+        if (STREAM) {
+            if (inflight)
+                mbar_wait(&full[0], par);
+            inflight = false;
+        } else if (!loaded && ntiles > 0) {
             mbar_wait(&full[0], 0);
+        }
+    }
+
+    // V[class gid][16 g + 4 qd + t] = W / sd for this warp's column groups, and the warp's part of
+    // the offset o[class] = sum_j mean[j] V[class][j] -> scr
+    __device__ __forceinline__ void load_v(const double *xcur, double (&wreg)[NBG * 4], int warp, int qd, int gid,
+                                           int dimp, int ngroups)
+    {
+        double pb = 0.0;
+#pragma unroll
+        for (int i = 0; i < NBG; ++i) {
+            const int g = warp + kDmmaWarps * i;
+            const int col = 16 * g + 4 * qd;
+            double2 w01 = make_double2(0.0, 0.0), w23 = w01, s01 = w01, s23 = w01, m01 = w01, m23 = w01;
+            if (g < ngroups) {
+                s01 = *reinterpret_cast<const double2 *>(sinvsd + col);
+                s23 = *reinterpret_cast<const double2 *>(sinvsd + col + 2);
+                m01 = *reinterpret_cast<const double2 *>(smean + col);
+                m23 = *reinterpret_cast<const double2 *>(smean + col + 2);
+                if (gid < P.C) {
+                    const double *wg = xcur + (size_t)gid * dimp + col;
+                    w01 = __ldcg(reinterpret_cast<const double2 *>(wg));
+                    w23 = __ldcg(reinterpret_cast<const double2 *>(wg + 2));
+                }
+            }
+            wreg[4 * i + 0] = w01.x * s01.x;
+            wreg[4 * i + 1] = w01.y * s01.y;
+            wreg[4 * i + 2] = w23.x * s23.x;
+            wreg[4 * i + 3] = w23.y * s23.y;
+            pb += m01.x * wreg[4 * i + 0];
+            pb += m01.y * wreg[4 * i + 1];
+            pb += m23.x * wreg[4 * i + 2];
+            pb += m23.y * wreg[4 * i + 3];
+        }
+        pb += __shfl_xor_sync(0xffffffffu, pb, 1);
+        pb += __shfl_xor_sync(0xffffffffu, pb, 2);
+        if (qd == 0)
+            scr[warp * 8 + gid] = pb;
+    }
+
+    // softmax of the rows of `nt` tiles (all warps; the CTA's rows row0 .. of the block): residuals
+    // over K-slice 0 of the partial logits, NLL into facc
+    __device__ __forceinline__ void softmax_tiles(int nt, int row0, int warp, int qd, int gid, double &facc)
+    {
+        double *rres = plog;
+        double o0 = 0.0, o1 = 0.0;
+#pragma unroll
+        for (int w8 = 0; w8 < kDmmaWarps; ++w8) {
+            o0 += scr[w8 * 8 + 2 * qd];
+            o1 += scr[w8 * 8 + 2 * qd + 1];
+        }
+#pragma unroll 2
+        for (int j = warp; j < nt; j += kWarps) {
+            const int lr = kTileRows * j + gid;
+            const bool rv = row0 + lr < r1;
+            const int cls = sy[lr];      // -1 and weight 0 beyond the CTA's last row
+            const double wi = sw[lr];
+            double2 v = *reinterpret_cast<const double2 *>(plog + (size_t)lr * 8 + 2 * qd);
+#pragma unroll
+            for (int w8 = 1; w8 < kDmmaWarps; ++w8) {
+                const double2 pv =
+                    *reinterpret_cast<const double2 *>(plog + ((size_t)w8 * cap8 + lr) * 8 + 2 * qd);
+                v.x += pv.x;
+                v.y += pv.y;
+            }
+            v.x -= o0;
+            v.y -= o1;
+            double mx = -INFINITY;
+            if (2 * qd < P.C)
+                mx = fmax(mx, v.x);
+            if (2 * qd + 1 < P.C)
+                mx = fmax(mx, v.y);
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            const double e0 = (2 * qd < P.C) ? exp(v.x - mx) : 0.0;
+            const double e1 = (2 * qd + 1 < P.C) ? exp(v.y - mx) : 0.0;
+            double den = e0 + e1;
+            den += __shfl_xor_sync(0xffffffffu, den, 1);
+            den += __shfl_xor_sync(0xffffffffu, den, 2);
+            double rr0 = wi * (e0 / den), rr1 = wi * (e1 / den);
+            if (2 * qd == cls)
+                rr0 -= wi;
+            if (2 * qd + 1 == cls)
+                rr1 -= wi;
+            *reinterpret_cast<double2 *>(rres + (size_t)lr * 8 + 2 * qd) =
+                rv ? make_double2(rr0, rr1) : make_double2(0.0, 0.0);
+            const double logden = log(den);
+            if (rv && 2 * qd == cls)
+                facc -= wi * ((v.x - mx) - logden);
+            if (rv && 2 * qd + 1 == cls)
+                facc -= wi * ((v.y - mx) - logden);
+        }
+    }
+
+    // mean / sd correction of HG column groups' accumulators (groups gbase .. of this warp) and the
+    // store of this CTA's partial gradient
+    __device__ __forceinline__ void store_groups(const double (&acc)[HG][2][2], int gbase, int warp, int qd, int gid,
+                                                 int dimp, int ngroups)
+    {
+        const double sc = scr[kDmmaWarps * 8 + gid];
+        double *gp = P.gpart + ((size_t)blk * P.Gmax + cta) * P.npad + (size_t)gid * dimp;
+#pragma unroll
+        for (int i = 0; i < HG; ++i) {
+            const int g = warp + kDmmaWarps * (gbase + i);
+            const int col = 16 * g + 4 * qd;
+            if (g < ngroups) {
+                const double2 s01 = *reinterpret_cast<const double2 *>(sinvsd + col);
+                const double2 s23 = *reinterpret_cast<const double2 *>(sinvsd + col + 2);
+                const double2 m01 = *reinterpret_cast<const double2 *>(smean + col);
+                const double2 m23 = *reinterpret_cast<const double2 *>(smean + col + 2);
+                double2 *dst = reinterpret_cast<double2 *>(gp + col);
+                __stcg(dst, make_double2((acc[i][0][0] - m01.x * sc) * s01.x,
+                                         (acc[i][1][0] - m01.y * sc) * s01.y));
+                __stcg(dst + 1, make_double2((acc[i][0][1] - m23.x * sc) * s23.x,
+                                             (acc[i][1][1] - m23.y * sc) * s23.y));
+            }
+        }
     }
 
     __device__ double eval(const double *xcur)
     {
+        if (STREAM)
+            return eval_panels(xcur);
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         const int qd = lane & 3, gid = lane >> 2;
         const int dimp = P.dimp;
@@ -211,81 +464,16 @@ struct PackedEval {
 
         // ---------------- pass 1: partial logits of every tile ----------------
         if (dmma_warp) {
-            // V[class gid][16 g + 4 qd + t] = W / sd for this warp's column groups, and the warp's
-            // part of the offset o[class] = sum_j mean[j] V[class][j]
             double wreg[NBG * 4];
-            double pb = 0.0;
-#pragma unroll
-            for (int i = 0; i < NBG; ++i) {
-                const int g = warp + kDmmaWarps * i;
-                const int col = 16 * g + 4 * qd;
-                double2 w01 = make_double2(0.0, 0.0), w23 = w01, s01 = w01, s23 = w01, m01 = w01, m23 = w01;
-                if (g < ngroups) {
-                    s01 = *reinterpret_cast<const double2 *>(sinvsd + col);
-                    s23 = *reinterpret_cast<const double2 *>(sinvsd + col + 2);
-                    m01 = *reinterpret_cast<const double2 *>(smean + col);
-                    m23 = *reinterpret_cast<const double2 *>(smean + col + 2);
-                    if (gid < P.C) {
-                        const double *wg = xcur + (size_t)gid * dimp + col;
-                        w01 = __ldcg(reinterpret_cast<const double2 *>(wg));
-                        w23 = __ldcg(reinterpret_cast<const double2 *>(wg + 2));
-                    }
-                }
-                wreg[4 * i + 0] = w01.x * s01.x;
-                wreg[4 * i + 1] = w01.y * s01.y;
-                wreg[4 * i + 2] = w23.x * s23.x;
-                wreg[4 * i + 3] = w23.y * s23.y;
-                pb += m01.x * wreg[4 * i + 0];
-                pb += m01.y * wreg[4 * i + 1];
-                pb += m23.x * wreg[4 * i + 2];
-                pb += m23.y * wreg[4 * i + 3];
-            }
-            pb += __shfl_xor_sync(0xffffffffu, pb, 1);
-            pb += __shfl_xor_sync(0xffffffffu, pb, 2);
-            if (qd == 0)
-                scr[warp * 8 + gid] = pb;
+            load_v(xcur, wreg, warp, qd, gid, dimp, ngroups);
             SQW_EPROF(0)
             if (!loaded && ntiles > 0)
                 mbar_wait(&full[0], 0);
             SQW_EPROF(1)
             const int ngw = (ngroups - warp + kDmmaWarps - 1) / kDmmaWarps;  // groups of this warp
-            // One shared address per lane and tile, immediate offsets for the warp's groups; the
-            // loads are unconditional (an absent group reads bytes of the next row or, past the last
-            // row, of the partial-logit buffer: multiplied by a zero V fragment) and the next tile's
-            // words are in flight while this tile's DMMAs issue.
             const unsigned rows_s = smem_u32(rows) + (unsigned)(gid * rsq + 4 * qd + 16 * warp);
             const unsigned plw = smem_u32(plog) + (unsigned)((((size_t)warp * cap8 + gid) * 8 + 2 * qd) * 8);
-            const unsigned tstride = (unsigned)(kTileRows * rsq);
-            unsigned cur[NBG], nxt[NBG];
-#pragma unroll
-            for (int i = 0; i < NBG; ++i)
-                cur[i] = nxt[i] = (ntiles > 0) ? lds_u32(rows_s + 16u * kDmmaWarps * i) : 0u;
-#pragma unroll 2
-            for (int j = 0; j < ntiles; ++j) {
-                const unsigned nb_ = rows_s + (unsigned)min(j + 1, ntiles - 1) * tstride;
-#pragma unroll
-                for (int i = 0; i < NBG; ++i)
-                    nxt[i] = lds_u32(nb_ + 16u * kDmmaWarps * i);
-                double pa[4][2];
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    pa[c][0] = pa[c][1] = 0.0;
-#pragma unroll
-                for (int i = 0; i < NBG; ++i) {
-                    if (i >= NBG - 2 && i >= ngw)  // warp-uniform; an absent earlier group multiplies zeros
-                        break;
-                    dmma884(pa[0], cvt_byte(cur[i], 0), wreg[4 * i + 0]);
-                    dmma884(pa[1], cvt_byte(cur[i], 1), wreg[4 * i + 1]);
-                    dmma884(pa[2], cvt_byte(cur[i], 2), wreg[4 * i + 2]);
-                    dmma884(pa[3], cvt_byte(cur[i], 3), wreg[4 * i + 3]);
-                }
-                // lane holds the partial S[row gid][class 2 qd + {0, 1}]
-                sts_v2f64(plw + (unsigned)(kTileRows * 8 * 8) * j, (pa[0][0] + pa[1][0]) + (pa[2][0] + pa[3][0]),
-                          (pa[0][1] + pa[1][1]) + (pa[2][1] + pa[3][1]));
-#pragma unroll
-                for (int i = 0; i < NBG; ++i)
-                    cur[i] = nxt[i];
-            }
+            packed_pass1_tiles<kDmmaWarps, NBG>(wreg, rows_s, plw, (unsigned)(kTileRows * rsq), ntiles, ngw);
         }
         loaded = true;
         __syncthreads();
@@ -293,63 +481,13 @@ struct PackedEval {
 
         // ---------------- softmax of every row (all 11 warps): residuals, NLL ----------------
         double facc = 0.0;
-        {
-            double o0 = 0.0, o1 = 0.0;
-#pragma unroll
-            for (int w8 = 0; w8 < kDmmaWarps; ++w8) {
-                o0 += scr[w8 * 8 + 2 * qd];
-                o1 += scr[w8 * 8 + 2 * qd + 1];
-            }
-#pragma unroll 2
-            for (int j = warp; j < ntiles; j += kWarps) {
-                const int lr = kTileRows * j + gid;
-                const bool rv = r0 + lr < r1;
-                const int cls = sy[lr];      // -1 and weight 0 beyond the CTA's last row
-                const double wi = sw[lr];
-                double2 v = *reinterpret_cast<const double2 *>(plog + (size_t)lr * 8 + 2 * qd);
-#pragma unroll
-                for (int w8 = 1; w8 < kDmmaWarps; ++w8) {
-                    const double2 pv =
-                        *reinterpret_cast<const double2 *>(plog + ((size_t)w8 * cap8 + lr) * 8 + 2 * qd);
-                    v.x += pv.x;
-                    v.y += pv.y;
-                }
-                v.x -= o0;
-                v.y -= o1;
-                double mx = -INFINITY;
-                if (2 * qd < P.C)
-                    mx = fmax(mx, v.x);
-                if (2 * qd + 1 < P.C)
-                    mx = fmax(mx, v.y);
-                mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-                mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-                const double e0 = (2 * qd < P.C) ? exp(v.x - mx) : 0.0;
-                const double e1 = (2 * qd + 1 < P.C) ? exp(v.y - mx) : 0.0;
-                double den = e0 + e1;
-                den += __shfl_xor_sync(0xffffffffu, den, 1);
-                den += __shfl_xor_sync(0xffffffffu, den, 2);
-                double rr0 = wi * (e0 / den), rr1 = wi * (e1 / den);
-                if (2 * qd == cls)
-                    rr0 -= wi;
-                if (2 * qd + 1 == cls)
-                    rr1 -= wi;
-                *reinterpret_cast<double2 *>(rres + (size_t)lr * 8 + 2 * qd) =
-                    rv ? make_double2(rr0, rr1) : make_double2(0.0, 0.0);
-                const double logden = log(den);
-                if (rv && 2 * qd == cls)
-                    facc -= wi * ((v.x - mx) - logden);
-                if (rv && 2 * qd + 1 == cls)
-                    facc -= wi * ((v.y - mx) - logden);
-            }
-        }
+        softmax_tiles(ntiles, r0, warp, qd, gid, facc);
         __syncthreads();
         SQW_EPROF(3)
 
         // ---------------- pass 2: G += R^T n over every tile, then the mean / sd correction and
         // the store of the CTA's partial gradient. The accumulators of HG = 6 column groups per
         // warp live in registers; a warp with 12 groups (two CTAs per SM) makes two sweeps.
-        constexpr int HG = 6, NH = NBG / HG;
-        static_assert(NBG % HG == 0, "column groups per warp");
         const int ngw = dmma_warp ? (ngroups - warp + kDmmaWarps - 1) / kDmmaWarps : 0;
 #pragma unroll
         for (int hh = 0; hh < NH; ++hh) {
@@ -363,50 +501,8 @@ struct PackedEval {
                 const unsigned rs_ = smem_u32(rres) + (unsigned)((qd * 8 + gid) * 8);
                 const unsigned xs_ = smem_u32(rows) +
                                      (unsigned)(qd * rsq + 2 * gid + 16 * warp + 16 * kDmmaWarps * hh * HG);
-                const unsigned half = (unsigned)(4 * rsq), tstride = (unsigned)(kTileRows * rsq);
-                double a0 = lds_f64(rs_), a1 = lds_f64(rs_ + 4 * 8 * 8), na0 = a0, na1 = a1;
-                unsigned x0[HG], x1[HG], nx0[HG], nx1[HG];
-#pragma unroll
-                for (int i = 0; i < HG; ++i) {
-                    x0[i] = nx0[i] = lds_u16(xs_ + 16u * kDmmaWarps * i);
-                    x1[i] = nx1[i] = lds_u16(xs_ + half + 16u * kDmmaWarps * i);
-                }
-#pragma unroll 2
-                for (int j = 0; j < ntiles; ++j) {
-                    // operands of the next tile (clamped on the last) ahead of this tile's DMMAs
-                    const int jn = min(j + 1, ntiles - 1);
-                    const unsigned rn = rs_ + (unsigned)(kTileRows * 8 * 8) * jn, xn = xs_ + tstride * jn;
-                    na0 = lds_f64(rn);                  // R[row qd][class gid]
-                    na1 = lds_f64(rn + 4 * 8 * 8);      // R[row 4+qd][class gid]
-#pragma unroll
-                    for (int i = 0; i < HG; ++i) {
-                        nx0[i] = lds_u16(xn + 16u * kDmmaWarps * i);
-                        nx1[i] = lds_u16(xn + half + 16u * kDmmaWarps * i);
-                    }
-                    // rows 0..3 of every group first, then rows 4..7: an accumulator is re-used at a
-                    // distance of 2 HG DMMAs (latency 26 cycles, issue 16)
-#pragma unroll
-                    for (int i = 0; i < HG; ++i) {
-                        if (hh * HG + i >= NBG - 2 && hh * HG + i >= ngw)  // warp-uniform
-                            break;
-                        dmma884(acc[i][0], a0, cvt_byte(x0[i], 0));
-                        dmma884(acc[i][1], a0, cvt_byte(x0[i], 1));
-                    }
-#pragma unroll
-                    for (int i = 0; i < HG; ++i) {
-                        if (hh * HG + i >= NBG - 2 && hh * HG + i >= ngw)
-                            break;
-                        dmma884(acc[i][0], a1, cvt_byte(x1[i], 0));
-                        dmma884(acc[i][1], a1, cvt_byte(x1[i], 1));
-                    }
-                    a0 = na0;
-                    a1 = na1;
-#pragma unroll
-                    for (int i = 0; i < HG; ++i) {
-                        x0[i] = nx0[i];
-                        x1[i] = nx1[i];
-                    }
-                }
+                packed_pass2_tiles<kDmmaWarps, NBG, HG>(acc, rs_, xs_, (unsigned)(4 * rsq),
+                                                        (unsigned)(kTileRows * rsq), ntiles, hh * HG, ngw);
             }
             if (hh == 0) {
                 // lane holds sum_i R[i][class gid] n[i][16 g + 4 qd + 2 e + h] in acc[i][h][e]; column 0
@@ -417,30 +513,84 @@ struct PackedEval {
                 SQW_EPROF(5)
             }
             // mean / sd correction, partial gradient of this CTA
-            if (dmma_warp && gid < P.C) {
-                const double sc = scr[kDmmaWarps * 8 + gid];
-                double *gp = P.gpart + ((size_t)blk * P.Gmax + cta) * P.npad + (size_t)gid * dimp;
-#pragma unroll
-                for (int i = 0; i < HG; ++i) {
-                    const int g = warp + kDmmaWarps * (hh * HG + i);
-                    const int col = 16 * g + 4 * qd;
-                    if (g < ngroups) {
-                        const double2 s01 = *reinterpret_cast<const double2 *>(sinvsd + col);
-                        const double2 s23 = *reinterpret_cast<const double2 *>(sinvsd + col + 2);
-                        const double2 m01 = *reinterpret_cast<const double2 *>(smean + col);
-                        const double2 m23 = *reinterpret_cast<const double2 *>(smean + col + 2);
-                        double2 *dst = reinterpret_cast<double2 *>(gp + col);
-                        __stcg(dst, make_double2((acc[i][0][0] - m01.x * sc) * s01.x,
-                                                 (acc[i][1][0] - m01.y * sc) * s01.y));
-                        __stcg(dst + 1, make_double2((acc[i][0][1] - m23.x * sc) * s23.x,
-                                                     (acc[i][1][1] - m23.y * sc) * s23.y));
-                    }
-                }
-            }
+            if (dmma_warp && gid < P.C)
+                store_groups(acc, hh * HG, warp, qd, gid, dimp, ngroups);
         }
         SQW_EPROF(7)
 #undef SQW_EPROF
         return facc;  // per-thread NLL partial
+    }
+
+    // STREAM: the three phases panel by panel; accumulators and V fragments stay in registers
+    __device__ double eval_panels(const double *xcur)
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int qd = lane & 3, gid = lane >> 2;
+        const int dimp = P.dimp;
+        const int ngroups = dimp >> 4;
+        const bool dmma_warp = warp < kDmmaWarps;
+        const int ngw = dmma_warp ? (ngroups - warp + kDmmaWarps - 1) / kDmmaWarps : 0;
+        double wreg[NBG * 4];
+        double acc[HG][2][2];
+#pragma unroll
+        for (int i = 0; i < HG; ++i)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                acc[i][h][0] = acc[i][h][1] = 0.0;
+        if (dmma_warp)
+            load_v(xcur, wreg, warp, qd, gid, dimp, ngroups);
+        double facc = 0.0;
+        const unsigned tstride = (unsigned)(kTileRows * rsq);
+        for (int p = 0; p < npan; ++p) {
+            const int pr0 = r0 + p * cap8;
+            const int nt = (min(cap8, r1 - pr0) + kTileRows - 1) / kTileRows;
+            // (the buffer, the partial logits and sw / sy are free: every warp passed the barrier that
+            // ended the previous panel's - or the previous evaluation's - pass 2)
+            if (have != p) {
+                if (threadIdx.x == 0)
+                    load_panel(p);
+                have = p;
+                inflight = true;
+            }
+            for (int i = threadIdx.x; i < nt * kTileRows; i += kThreads) {
+                const bool rv = pr0 + i < r1;
+                sw[i] = rv ? __ldg(P.w + (size_t)blk * P.nb + pr0 + i) : 0.0;
+                sy[i] = rv ? __ldg(P.y + (size_t)blk * P.nb + pr0 + i) : -1;
+            }
+            if (dmma_warp) {
+                if (inflight)
+                    mbar_wait(&full[0], par);
+                const unsigned rows_s = smem_u32(rows) + (unsigned)(gid * rsq + 4 * qd + 16 * warp);
+                const unsigned plw = smem_u32(plog) + (unsigned)((((size_t)warp * cap8 + gid) * 8 + 2 * qd) * 8);
+                packed_pass1_tiles<kDmmaWarps, NBG>(wreg, rows_s, plw, tstride, nt, ngw);
+            }
+            if (inflight)
+                par ^= 1u;
+            inflight = false;
+            __syncthreads();
+            softmax_tiles(nt, pr0, warp, qd, gid, facc);
+            __syncthreads();
+            if (dmma_warp && ngw > 0) {
+                const unsigned rs_ = smem_u32(plog) + (unsigned)((qd * 8 + gid) * 8);
+                const unsigned xs_ = smem_u32(rows) + (unsigned)(qd * rsq + 2 * gid + 16 * warp);
+                packed_pass2_tiles<kDmmaWarps, NBG, HG>(acc, rs_, xs_, (unsigned)(4 * rsq), tstride, nt, 0, ngw);
+            }
+            if (p + 1 < npan)
+                __syncthreads();
+        }
+        // column 0 of the accumulated product is the class sum of the residuals over ALL panels
+        if (warp == 0 && qd == 0)
+            scr[kDmmaWarps * 8 + gid] = acc[0][0][0];
+        __syncthreads();
+        if (npan > 1) {   // the next evaluation starts with panel 0: fetch it behind the solver's chain
+            if (threadIdx.x == 0)
+                load_panel(0);
+            have = 0;
+            inflight = true;
+        }
+        if (dmma_warp && gid < P.C)
+            store_groups(acc, 0, warp, qd, gid, dimp, ngroups);
+        return facc;
     }
 };
 

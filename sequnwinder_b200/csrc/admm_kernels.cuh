@@ -46,6 +46,9 @@ __device__ __forceinline__ int ld_volatile_int(const int *p)
 //           matrices of any row length, up to 24 classes, blocks of any size (cfg-3, cfg-4).
 //   MODE 11 MODE 10 for C = 8 NCT + 1 classes (2^k labels + one outgroup class, cfg-4): NCT class
 //           tiles of DMMAs and the last class as DFMAs on the operands the DMMA path converted.
+//   MODE 12 MODE 8 for CTAs that own more rows than shared memory holds (CTA budgets, blocks of
+//           many short rows): the rows pass through the buffer panel by panel, one fetch per
+//           evaluation, the gradient accumulators in registers across the panels.
 //   MODE 9  MODE 8 with two CTAs of 192 threads per SM (4 DMMA + 2 helper warps each): the CTAs of
 //           an SM belong to different ADMM blocks, so one evaluates while the other sits in its
 //           solver's exchange chain.
@@ -94,6 +97,10 @@ struct EvalSelect<NCT, 10> {  // packed counts streamed from HBM, column-chunked
 template <int NCT>
 struct EvalSelect<NCT, 11> {  // the same for C = 8 NCT + 1 classes: the last class rides along as DFMAs
     typedef PackedChunkEval<NCT, true> type;
+};
+template <int NCT>
+struct EvalSelect<NCT, 12> {  // packed counts streamed PANEL by panel through the resident form's buffer
+    typedef PackedEval<NCT, 8, kThreads, true> type;
 };
 template <int NCT>
 struct EvalSelect<NCT, 9> {   // the same with two CTAs of 192 threads per SM
@@ -377,7 +384,7 @@ admm_xupdate_kernel(AdmmDev P, TileSmemLayout L, int phase, int eval_cap)
     ws.cta = cta;
     ws.prof = P.prof ? s_prof : nullptr;
     // modes 4/5 keep W in registers: the head of the dynamic shared memory is the slice cache
-    ws.slice = ((MODE == 4 || MODE == 5 || MODE == 8 || MODE == 9 || MODE == 10 || MODE == 11) && NCT == 1)
+    ws.slice = ((MODE == 4 || MODE == 5 || MODE == 8 || MODE == 9 || MODE == 10 || MODE == 11 || MODE == 12) && NCT == 1)
                    ? reinterpret_cast<double *>(smem_raw) : nullptr;
     int status = 0;
     bool finished = false;
@@ -908,7 +915,7 @@ admm_eval_kernel(AdmmDev P, TileSmemLayout L, double pho, double *f_out)
     BlockProblem<Eval> prob{P, blk, cta, P.G, pho, P.ut + (size_t)blk * P.upad, ev,
                             P.leaf_edge_ptr, P.edge_par};
     double fpart = prob.eval_partial(xt);
-    if (MODE == 4 || MODE == 5 || MODE == 6 || MODE == 8 || MODE == 9 || MODE == 10 || MODE == 11) {
+    if (MODE == 4 || MODE == 5 || MODE == 6 || MODE == 8 || MODE == 9 || MODE == 10 || MODE == 11 || MODE == 12) {
         // further evaluations exercise the ring wrap-around / resident path; results must agree
         for (int rep = 0; rep < 2; ++rep) {
             __syncthreads();

@@ -304,13 +304,15 @@ class LOneCuda(Optimizer):
         other.sm_Debug = self.sm_Debug
         other._counts, other._counts_dev = self._counts, self._counts_dev
 
-    def sweep_concurrent(self, ridges, slots: int = 3):
+    def sweep_concurrent(self, ridges, slots: int = 4):
         """The regularisation sweep with ``slots`` trainings side by side on one GPU: ``slots``
         worker threads, each with its own optimizer whose x-update launches are capped at
         148 // slots CTAs (``setCtaBudget``), take the lambda values from a queue. A block's group
         of CTAs shrinks with the budget, and with it the part of every L-BFGS trip that is exchange
-        between CTAs; measured on B200 at cfg-2: 1.18x (2 slots), 1.29x (3), 1.23x (4), 0.70x (8)
-        against ``sweep``. Returns [(x, sm_x, stats, log)] in the order of ``ridges``; each entry
+        between CTAs; measured on B200 at cfg-2, 16 lambda values: from the count matrix (rows panel
+        by panel through shared memory, MODE 12) 31.4 s with 3 slots, 29.3 s with 4, 38.2 s with 6,
+        against 38.2 s for ``sweep``; from the fp64 matrix 1.18x (2 slots), 1.29x (3), 1.23x (4),
+        0.70x (8) against ``sweep``. Returns [(x, sm_x, stats, log)] in the order of ``ridges``; each entry
         is bit-identical to a single optimizer run with the same CTA budget, and equal to
         ``sweep``'s entry up to the rounding of a different summation order of the partial
         gradients."""

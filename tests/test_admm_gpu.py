@@ -507,7 +507,8 @@ def test_packed_trainer_matches_oracle_fixed_iterations(oracle, monkeypatch, cfg
 
 def test_counts_with_a_cta_budget_use_the_streamed_packed_kernels(oracle):
     """A handle with a CTA budget (concurrent sweeps) has too few CTAs per block for its rows to stay
-    in shared memory: the count matrix runs through the streamed packed kernels (MODE 10)."""
+    in shared memory: the count matrix passes through the resident form's buffer panel by panel
+    (MODE 12; 250 rows per CTA here = two panels)."""
     p = make_problem("cfg2", 4000)
     T, A, S = 8, 3, 1
     xo, smo, tr = oracle.lone_execute(p.x0, p.smx0, p.data, p.cls, p.weights, p.st, p.num_classes,
@@ -519,9 +520,73 @@ def test_counts_with_a_cta_budget_use_the_streamed_packed_kernels(oracle):
     lo.setNumClasses(p.num_classes); lo.setNumPredictors(p.data.shape[1] - 1)
     lo.setPho(1.7); lo.set_numThreads(T); lo.initUandZ(); lo.setCtaBudget(16)
     lo.execute()
-    assert lo.stats.eval_mode == 10 and lo.stats.ctas_per_block == 2
+    assert lo.stats.eval_mode == 12 and lo.stats.ctas_per_block == 2
+    assert lo.stats.tiles_per_cta > lo.stats.ring_stages      # more rows per CTA than one panel holds
     assert np.array_equal(lo.log.nfev, tr.log_nfev[:, opt.java_block_order(T)])
     assert _rel(lo.getX(), xo) <= REL_TOL
+
+
+# --------------------------------------------------------------------------------------------
+# MODE 12: MODE 8's inner loops on rows that pass through shared memory panel by panel. Forced on
+# small shapes with SQW_ADMM_PACKED_MODE=12 and a small panel (SQW_ADMM_PANEL_ROWS) so that a CTA
+# sees several panels, the last one partial.
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg,n,mf,T,panel", [("cfg1", 500, 60, 5, 8), ("cfg2", 4000, None, 8, 8),
+                                                ("cfg2", 4000, None, 8, 24), ("cfg1", 301, 24, 7, 8),
+                                                ("cfg2", 20000, None, 8, 48)])
+def test_packed_panel_evaluation_matches_oracle(oracle, monkeypatch, cfg, n, mf, T, panel):
+    monkeypatch.setenv("SQW_ADMM_PACKED_MODE", "12")
+    monkeypatch.setenv("SQW_ADMM_PANEL_ROWS", str(panel))
+    p = make_problem(cfg, n, max_features=mf)
+    nrow, dim = p.data.shape
+    C, NN = p.num_classes, p.st.num_nodes
+    rng = np.random.default_rng(5)
+    cx = rng.normal(size=(T, C * dim)) * 0.05
+    smx = rng.normal(size=NN * dim) * 0.05
+    # (the evaluation kernel runs three evaluations and returns NaN unless they agree bit for bit:
+    # panel re-loads and the prefetch of panel 0 behind an evaluation are part of the check)
+    f, g = opt.block_evaluate(None, p.cls, p.weights, p.crs, C, T, cx, smx, 1.7, counts=packed_counts(p))
+    nb = nrow // T
+    zd = np.zeros(NN * NN * dim)
+    for b, t in enumerate(opt.java_block_order(T)):
+        rows = np.arange(nb) * T + t
+        fo, go = oracle.eval_fg(p.data[rows], p.cls[rows], p.weights[rows], cx[b], smx, zd, zd, 1.7,
+                                p.st, C)
+        assert abs(f[b] - fo) <= 1e-12 * abs(fo)
+        assert np.abs(g[b] - go).max() <= 1e-12 * np.abs(go).max()
+
+
+@pytest.mark.parametrize("cfg,n,mf,T,A,S,panel,budget", [
+    ("cfg1", 500, 60, 5, 50, 3, 8, 0),
+    ("cfg2", 4000, None, 8, 4, 1, 8, 0),
+    ("cfg1", 301, 24, 7, 8, 2, 8, 0),
+    ("cfg2", 20000, None, 8, 1, 1, 0, 49),     # a slot of a three-way concurrent sweep at the benchmark's shape
+    ("cfg2", 20000, None, 8, 1, 1, 0, 24),     # ... of a six-way one: 834 rows per CTA, six panels
+])
+def test_packed_panel_trainer_matches_oracle(oracle, monkeypatch, cfg, n, mf, T, A, S, panel, budget):
+    if panel:
+        monkeypatch.setenv("SQW_ADMM_PACKED_MODE", "12")
+        monkeypatch.setenv("SQW_ADMM_PANEL_ROWS", str(panel))
+    p = make_problem(cfg, n, max_features=mf)
+    xo, smo, tr = oracle.lone_execute(p.x0, p.smx0, p.data, p.cls, p.weights, p.st, p.num_classes,
+                                      num_threads=T, admm_max_itr=A, nodes_max_itr=S, host_threads=8)
+    lo = opt.LOneCuda(p.x0.copy(), p.smx0.copy(), None)
+    lo.setCountMatrix(*packed_counts(p))
+    lo.setRidge(10.0); lo.setADMMmaxItrs(A); lo.setBGFSmaxItrs(-1); lo.setSeqUnwinderMaxIts(S)
+    lo.setClassStructure(p.crs); lo.setClsMembership(p.cls); lo.setInstanceWeights(p.weights)
+    lo.setNumClasses(p.num_classes); lo.setNumPredictors(p.data.shape[1] - 1)
+    lo.setPho(1.7); lo.set_numThreads(T); lo.initUandZ()
+    if budget:
+        lo.setCtaBudget(budget)
+    lo.execute()
+    assert lo.stats.eval_mode == 12
+    if budget:
+        assert lo.stats.tiles_per_cta > lo.stats.ring_stages
+    assert lo.stats.outer_iters == tr.outer_iters
+    assert lo.log.admm_iters == tr.admm_iters
+    assert np.array_equal(lo.log.nfev, tr.log_nfev[:, opt.java_block_order(T)])
+    assert _rel(lo.getX(), xo) <= REL_TOL
+    assert _rel(lo.getsmX(), smo) <= REL_TOL
 
 
 def test_packed_ridge_sweep_and_resident_reuse(oracle):

@@ -14,6 +14,8 @@ if packed:
 lo.setRidge(10.0); lo.setADMMmaxItrs(A); lo.setSeqUnwinderMaxIts(S)
 lo.setClassStructure(p.crs); lo.setClsMembership(p.cls); lo.setInstanceWeights(p.weights)
 lo.setNumClasses(p.num_classes); lo.setNumPredictors(p.data.shape[1]-1); lo.setPho(1.7); lo.set_numThreads(T)
+if os.environ.get('SQW_BUDGET'):   # a slot of a concurrent sweep: at most this many CTAs
+    lo.setCtaBudget(int(os.environ['SQW_BUDGET']))
 t0 = time.time(); lo.execute(); t_gpu = time.time() - t0
 s = lo.stats
 print('mode', s.eval_mode, end=' '); print('gpu: outer', s.outer_iters, 'conv', s.converged, 'admm', lo.log.admm_iters, 'evals', s.total_evals, 'wall %.2fs dev total %.3fs admm %.3fs xupdate %.3fs launches %d pho %.4g' % (t_gpu, s.seconds_total, s.seconds_admm, s.seconds_eval, s.launches, s.final_pho), flush=True)
