@@ -178,6 +178,25 @@ struct BlockProblem {
         data_issue(k, v);
         return data_finish(k, v);
     }
+    // The same sum for a group of at most kSmallBatch CTAs (a handle with a CTA budget): same
+    // order, a third of the registers - the solver's loop over a thread's further coordinates
+    // keeps all of a coordinate's loads in flight instead of spilling the first ones to make room.
+    static constexpr int kSmallBatch = 8;
+    __device__ void data_issue_small(int k, double (&v)[kSmallBatch])
+    {
+        const double *gp = P.gpart + (size_t)blk * P.Gmax * P.npad + k;
+#pragma unroll
+        for (int j = 0; j < kSmallBatch; ++j)
+            v[j] = (j < G) ? __ldcg(gp + (size_t)j * P.npad) : 0.0;
+    }
+    __device__ double data_finish_small(int, double (&v)[kSmallBatch])
+    {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < kSmallBatch; ++j)
+            s += v[j];
+        return s;
+    }
 
     // augmented Lagrangian term rho*(x - sm_x[par] - z + u_t) of coordinate k for w >= 1
     // (LOne.java:982-998); faug accumulates rho/2 * (...)^2 (LOne.java:1031-1047). xk = x[k].
@@ -942,9 +961,11 @@ struct RosenProblem {
     int n;
     __device__ double eval_partial(const double *) { return 0.0; }
     const double *x;
-    static constexpr int kBatch = 1;
+    static constexpr int kBatch = 1, kSmallBatch = 1;
     __device__ void data_issue(int, double (&)[kBatch]) {}
     __device__ double data_finish(int, double (&)[kBatch]) { return 0.0; }
+    __device__ void data_issue_small(int, double (&)[kSmallBatch]) {}
+    __device__ double data_finish_small(int, double (&)[kSmallBatch]) { return 0.0; }
     __device__ bool aug_load(int, double (&)[6], int &) { return false; }
     __device__ double aug_term_cached(double, const double (&)[6], int, double &) { return 0.0; }
     __device__ double aug_term(int k, double, double &facc)

@@ -806,13 +806,25 @@ __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier 
             if (!cached)
                 ws.g[kf] = g0;
         }
-        for (int k = kf + NT; k < k1; k += NT) {  // (never with the slice cache)
-            CoordRegs c;
-            double v[Problem::kBatch], gk, yn;
-            prob.data_issue(k, v);
-            load_coord(k, c, false);
-            reduce_coord(k, c, prob.data_finish(k, v), gk, yn);
-            ws.g[k] = gk;
+        if (G <= Problem::kSmallBatch) {
+            // (a small group = a long slice: 2 - 3 coordinates per thread at 6 CTAs per block)
+            for (int k = kf + NT; k < k1; k += NT) {
+                CoordRegs c;
+                double v[Problem::kSmallBatch], gk, yn;
+                prob.data_issue_small(k, v);
+                load_coord(k, c, false);
+                reduce_coord(k, c, prob.data_finish_small(k, v), gk, yn);
+                ws.g[k] = gk;
+            }
+        } else {
+            for (int k = kf + NT; k < k1; k += NT) {  // (never with the slice cache)
+                CoordRegs c;
+                double v[Problem::kBatch], gk, yn;
+                prob.data_issue(k, v);
+                load_coord(k, c, false);
+                reduce_coord(k, c, prob.data_finish(k, v), gk, yn);
+                ws.g[k] = gk;
+            }
         }
         pd[D_F] += fpart;
         SQW_PROF2(0)
