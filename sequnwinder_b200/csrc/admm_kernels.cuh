@@ -251,12 +251,20 @@ struct BlockProblem {
             if (e1 - e0 > 2)
                 return false;
             ne = e1 - e0;
-            for (int j = 0; j < ne; ++j) {
-                const int e = e0 + j, par = epar[e];
-                const size_t o = (size_t)e * P.dimp + w;
-                a[3 * j] = (par >= 0) ? __ldg(P.smx + (size_t)par * P.dimp + w) : 0.0;
-                a[3 * j + 1] = __ldg(P.z + o);
-                a[3 * j + 2] = __ldcg(ut + o);
+            // (constant indices: a[] stays in registers; all loads are issued before any use)
+            const size_t o = (size_t)e0 * P.dimp + w;
+            const int par0 = (ne >= 1) ? epar[e0] : -1, par1 = (ne == 2) ? epar[e0 + 1] : -1;
+            if (par0 >= 0)
+                a[0] = __ldg(P.smx + (size_t)par0 * P.dimp + w);
+            if (par1 >= 0)
+                a[3] = __ldg(P.smx + (size_t)par1 * P.dimp + w);
+            if (ne >= 1) {
+                a[1] = __ldg(P.z + o);
+                a[2] = __ldcg(ut + o);
+            }
+            if (ne == 2) {
+                a[4] = __ldg(P.z + o + P.dimp);
+                a[5] = __ldcg(ut + o + P.dimp);
             }
         }
         return true;

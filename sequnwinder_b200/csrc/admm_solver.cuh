@@ -543,6 +543,9 @@ struct SolveWs {
                      // slice of x, d, g_old, wa, S, Y stays on chip for the whole launch
 };
 
+#ifndef SQW_AUG_FIRST
+#define SQW_AUG_FIRST 1   // phase R: the augmented term's loads ahead of the partials' (see the loop)
+#endif
 #ifndef SQW_AUG_CACHE
 #define SQW_AUG_CACHE 0   // keep the augmented term's inputs (sm_x, z, u_t of a coordinate's edges) on chip too:
                           // 6 of a coordinate's 24 loads per trip less; measured 59.8 vs 59.9 us per evaluation
@@ -674,7 +677,7 @@ __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier 
     status = 0;
 
     // operands of coordinate k for phase R (and U): everything but the phase-E partials
-    auto load_coord = [&](int k, CoordRegs &c, bool from_cache) {
+    auto load_coord = [&](int k, CoordRegs &c, bool from_cache, bool with_aug = true) {
         c.d = c.go = c.wa = 0.0;
 #pragma unroll
         for (int i = 0; i < kLbfgsM; ++i)
@@ -719,7 +722,7 @@ __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier 
             return;
         }
 #endif
-        c.gaug = prob.aug_term(k, c.x, c.faug);
+        c.gaug = with_aug ? prob.aug_term(k, c.x, c.faug) : 0.0;
     };
 
     for (int trip = 0;; ++trip) {
@@ -787,6 +790,17 @@ __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier 
         tk2 = tk0;
         if (mine) {
             double v[Problem::kBatch];
+#if SQW_AUG_FIRST
+            // The augmented term reads (sm_x[par], z, u_t) of the coordinate's one or two edges. Left
+            // inside load_coord, ptxas sinks these loads behind the wait for the partials and issues
+            // them in three dependent groups (sm_x | z, u | z', u': ncu source page).
+            // Fetched here, ahead of the partials, they share the partials' round trip; same
+            // operations in the same order. Measured A/B at cfg-2: 2.838 -> 2.822 s (sm_x and z hit
+            // L1, so only the two u_t round trips were saved); a 49-CTA handle 6.20 -> 6.24 s.
+            double aug_in[6];
+            int aug_ne = 0;
+            const bool aug_split = prob.aug_load(kf, aug_in, aug_ne);
+#endif
             prob.data_issue(kf, v);
 #if SQW_PROF_SPLIT
             // probe build: serialise the two groups of loads and stamp after each has arrived
@@ -799,6 +813,12 @@ __device__ int lbfgs_group_solve(Problem &prob, const SolveWs &ws, GroupBarrier 
                 tk2 += 1;
             SQW_PROF2(7)
             reduce_coord(kf, c0, dsum, g0, yn0);
+#elif SQW_AUG_FIRST
+            // (the loads of the augmented term were issued ahead of the partials', see above)
+            load_coord(kf, c0, cached, !aug_split);
+            if (aug_split)
+                c0.gaug = prob.aug_term_cached(c0.x, aug_in, aug_ne, c0.faug);
+            reduce_coord(kf, c0, prob.data_finish(kf, v), g0, yn0);
 #else
             load_coord(kf, c0, cached);
             reduce_coord(kf, c0, prob.data_finish(kf, v), g0, yn0);
