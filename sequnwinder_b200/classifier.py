@@ -214,8 +214,8 @@ def cross_validate(structure: ClassRelationStructure, counts: np.ndarray, cls: n
     """1 + len(folds) trainings. ``slots`` > 1 runs them side by side on one GPU, each on
     148 // slots CTAs (LOneCuda.setCtaBudget; DESIGN.md 2.5): the trainings are independent, so this
     is the job-level batching the reference's one-JVM-thread loop cannot do. Measured on B200 at
-    cfg-2 with 3 folds (count matrix, rows panel by panel through shared memory): 12.3 s with one
-    slot, 11.6 s with three, 9.3 s with four (all four trainings at once)."""
+    cfg-2 with 3 folds (count matrix, rows panel by panel through shared memory): 12.5 s with one
+    slot, 11.6 s with three, 8.7 s with four (all four trainings at once)."""
     import queue
     import threading
 

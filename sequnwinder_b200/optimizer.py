@@ -310,7 +310,7 @@ class LOneCuda(Optimizer):
         148 // slots CTAs (``setCtaBudget``), take the lambda values from a queue. A block's group
         of CTAs shrinks with the budget, and with it the part of every L-BFGS trip that is exchange
         between CTAs; measured on B200 at cfg-2, 16 lambda values: from the count matrix (rows panel
-        by panel through shared memory, MODE 12) 31.4 s with 3 slots, 29.3 s with 4, 38.2 s with 6,
+        by panel through shared memory, MODE 12) 28-31 s with 3 slots, 28-32 s with 4, 38.2 s with 6,
         against 38.2 s for ``sweep``; from the fp64 matrix 1.18x (2 slots), 1.29x (3), 1.23x (4),
         0.70x (8) against ``sweep``. Returns [(x, sm_x, stats, log)] in the order of ``ridges``; each entry
         is bit-identical to a single optimizer run with the same CTA budget, and equal to
