@@ -32,13 +32,21 @@ JNIEXPORT jstring JNICALL SQW_JNI(framework_LOneCuda, lastError)(JNIEnv *env, jc
 }
 
 /* set_structure + set_params from Java arrays; returns the new handle in *out */
+/* device >= 0: the GPU this training runs on (CUDA's current device is per host thread, and a JVM
+ * worker thread starts on device 0); ctaBudget > 0: at most that many CTAs per x-update launch, so
+ * that several LOneCuda.execute() calls on different Java threads train side by side on one GPU
+ * (the folds of a cross-validation, a regularisation sweep) */
 static jint open_handle(JNIEnv *env, jintArray nodeIndex, jintArray isLeaf, jintArray layer,
                         jintArray parentPtr, jintArray parentIdx, jintArray childPtr,
                         jintArray childIdx, jint numLayers, jdouble ridge, jdouble pho, jint threads,
-                        jint admmMaxItr, jint nodesMaxItr, jint debug, sqw_admm **out)
+                        jint admmMaxItr, jint nodesMaxItr, jint debug, jint device, jint ctaBudget,
+                        sqw_admm **out)
 {
     sqw_admm *h = NULL;
-    jint rc = sqw_admm_create(&h);
+    jint rc = (device >= 0) ? sqw_set_device(device) : SQW_OK;
+    if (rc != SQW_OK)
+        return rc;
+    rc = sqw_admm_create(&h);
     if (rc != SQW_OK)
         return rc;
     const jsize numNodes = (*env)->GetArrayLength(env, nodeIndex);
@@ -62,6 +70,8 @@ static jint open_handle(JNIEnv *env, jintArray nodeIndex, jintArray isLeaf, jint
     if (ni) (*env)->ReleaseIntArrayElements(env, nodeIndex, ni, JNI_ABORT);
     if (rc == SQW_OK)
         rc = sqw_admm_set_params(h, ridge, pho, threads, admmMaxItr, nodesMaxItr, debug);
+    if (rc == SQW_OK && ctaBudget > 0)
+        rc = sqw_admm_set_cta_budget(h, ctaBudget);   /* before set_problem: it sizes the groups */
     if (rc != SQW_OK) {
         sqw_admm_destroy(h);
         h = NULL;
@@ -88,12 +98,13 @@ JNIEXPORT jint JNICALL SQW_JNI(framework_LOneCuda, nativeTrain)(
     jintArray parentPtr, jintArray parentIdx, jintArray childPtr, jintArray childIdx, jint numLayers,
     jdoubleArray data, jlong nRows, jint dim, jint numClasses, jintArray cls, jdoubleArray weights,
     jdouble ridge, jdouble pho, jint threads, jint admmMaxItr, jint nodesMaxItr, jint debug,
-    jdoubleArray xInOut, jdoubleArray smxInOut)
+    jint device, jint ctaBudget, jdoubleArray xInOut, jdoubleArray smxInOut)
 {
     (void)klass;
     sqw_admm *h = NULL;
     jint rc = open_handle(env, nodeIndex, isLeaf, layer, parentPtr, parentIdx, childPtr, childIdx,
-                          numLayers, ridge, pho, threads, admmMaxItr, nodesMaxItr, debug, &h);
+                          numLayers, ridge, pho, threads, admmMaxItr, nodesMaxItr, debug, device,
+                          ctaBudget, &h);
     if (rc != SQW_OK)
         return rc;
     jint *y = (*env)->GetIntArrayElements(env, cls, NULL);
@@ -117,12 +128,14 @@ JNIEXPORT jint JNICALL SQW_JNI(framework_LOneCuda, nativeTrainCounts)(
     jintArray parentPtr, jintArray parentIdx, jintArray childPtr, jintArray childIdx, jint numLayers,
     jbyteArray counts, jdoubleArray mean, jdoubleArray sd, jlong nRows, jint dim, jint numClasses,
     jintArray cls, jdoubleArray weights, jdouble ridge, jdouble pho, jint threads, jint admmMaxItr,
-    jint nodesMaxItr, jint debug, jdoubleArray xInOut, jdoubleArray smxInOut)
+    jint nodesMaxItr, jint debug, jint device, jint ctaBudget, jdoubleArray xInOut,
+    jdoubleArray smxInOut)
 {
     (void)klass;
     sqw_admm *h = NULL;
     jint rc = open_handle(env, nodeIndex, isLeaf, layer, parentPtr, parentIdx, childPtr, childIdx,
-                          numLayers, ridge, pho, threads, admmMaxItr, nodesMaxItr, debug, &h);
+                          numLayers, ridge, pho, threads, admmMaxItr, nodesMaxItr, debug, device,
+                          ctaBudget, &h);
     if (rc != SQW_OK)
         return rc;
     jint *y = (*env)->GetIntArrayElements(env, cls, NULL);
