@@ -3,7 +3,7 @@ tools/gpu_nfev_dump.py): what a schedule of evaluation caps costs per ADMM itera
 Model (fitted to SQW_ADMM_PROFILE at cfg-2): a trip of a group of G CTAs costs
 eval(G) + solver(G); a launch costs a fixed overhead; a phase lasts as long as its slowest block."""
 import sys, itertools, numpy as np
-nf = np.load(sys.argv[1] if len(sys.argv) > 1 else 'gpurun_out/nfev_cfg2.npy').astype(int)
+nf = np.load(sys.argv[1] if len(sys.argv) > 1 else 'profiles/r02_nfev_cfg2.npy').astype(int)
 NB, NCTA, GCAP, ROWS = nf.shape[1], 144, 48, 2500
 TRIP = np.zeros(NB + 1)
 for act in range(1, NB + 1):

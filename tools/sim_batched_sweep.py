@@ -1,5 +1,5 @@
 """Cost model of the ways to run BASELINE config 5 (16 lambda values on the cfg-2 matrix) on one GPU, on
-the recorded per-block evaluation counts of a cfg-2 run (gpurun_out/nfev_cfg2.npy, tools/gpu_nfev_dump.py):
+the recorded per-block evaluation counts of a cfg-2 run (profiles/r02_nfev_cfg2.npy, written by tools/gpu_nfev_dump.py):
  * one training after the other on the whole GPU (checks the model: 814 us per iteration against 792 measured),
  * trainings side by side with static CTA budgets (what sweep_concurrent does),
  * ONE launch series over all (lambda, block) pairs with count-based, reproducible re-grouping (not built).
@@ -11,7 +11,7 @@ fewer than 17 CTAs per block a CTA's slice of the solver vectors no longer fits 
 reduce phase grows from 4.6 to 25 us, so the measured sweeps (31.4 / 29.3 s with 3 / 4 slots) are slower than
 the rows below (20-24 s) - and a single-launch batched solve would meet the same wall. DESIGN.md 2.5."""
 import numpy as np, sys
-nf = np.load(sys.argv[1] if len(sys.argv) > 1 else 'gpurun_out/nfev_cfg2.npy').astype(int)
+nf = np.load(sys.argv[1] if len(sys.argv) > 1 else 'profiles/r02_nfev_cfg2.npy').astype(int)
 ROWS=2500; CAPS=(8,12,16,20,26,10**9)
 def chain(G): return 13.1 + 0.07*(G-18) if G>1 else 6.0   # us; G=1: no cross-CTA barriers (guess 6)
 def ev8(r): return 10.4 + 0.0816*r
