@@ -945,7 +945,9 @@ static int plan_blocks(sqw_admm *h, int64_t n_rows, int32_t dim, int32_t num_cla
             } else {
                 // MODE 12: the CTA's rows pass through the resident form's buffer panel by panel; the
                 // panel is as large as shared memory allows (SQW_ADMM_PANEL_ROWS: test hook, smaller)
-                int cap = rows_cap8;
+                // (a row costs its bytes + 8 K-slices of partial logits + weight and class: start the
+                // search just above what the budget can hold)
+                int cap = (int)std::min<long long>(rows_cap8, (long long)(budget / (size_t)(dimp16 + 524)) / 8 * 8 + 8);
                 if (const char *pr = getenv("SQW_ADMM_PANEL_ROWS"))
                     cap = std::min(cap, std::max(8, atoi(pr) / 8 * 8));
                 while (cap > 8 && packed_smem_layout(dimp16, cap, kSolveSliceBytes).total > budget)
